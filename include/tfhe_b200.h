@@ -1,0 +1,156 @@
+/*
+ * tfhe_b200.h — C ABI of libtfhe_b200.so, the B200-native gate-bootstrapping engine.
+ *
+ * This is the drop-in boundary for ONE hot path of nucypher/TFHE.jl: bootstrapped gate
+ * evaluation (linear prologue -> modulus switch -> blind rotation -> sample extraction ->
+ * key switch), single-key and multi-key.  The reference (pure Julia) has no FFI; the seam is
+ * the set of Julia functions that gates.jl / mk_gates.jl call down into.  Each entry point
+ * below names the reference function it replaces (file:line under /root/reference/src).
+ * The Julia-side `ccall` binding is shown in INTEGRATION.md and shipped in
+ * tfhe.jl_b200/julia/TFHEB200.jl; tests bind the same symbols with Python ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative TFHE_B200_E* code otherwise; the text of
+ *     the last error is available from tfhe_b200_last_error() (no exceptions cross the ABI).
+ *   - all torus data are int32 (Torus32 = Int32, numeric-functions.jl:1), wrap-around mod 2^32.
+ *   - the caller owns every host buffer; the library owns device memory.  Host pointers may be
+ *     pageable.  *_dev variants take DEVICE pointers (inputs already resident in HBM) and a
+ *     cudaStream_t passed as void* (NULL = default stream); they are asynchronous.
+ *   - there is NO CPU fallback: without a CUDA device every call fails with TFHE_B200_ENODEV.
+ *   - calls on one context are serialised by an internal mutex; contexts are independent
+ *     (one context per GPU; gate batches shard across contexts with no collective).
+ *
+ * Layouts
+ *   LWE ciphertext batch     [count][n+1]            a[0..n-1], b   (lwe.jl:21-29); this is the
+ *                                                    memory of a Julia Matrix{Int32}(n+1, count)
+ *   extracted LWE batch      [count][N*k+1]          (tlwe.jl:55-59)
+ *   BK, coefficient domain   [n][l][k+1][k+1][N]     samples[r,j].a[c] (tgsw.jl:28), int32
+ *   KSK                      [N*k][t][base-1][n+1]   key[h,j,i] (keyswitch.jl:36-38), C order of
+ *                                                    Julia's column-major array, samples flattened
+ *   TLWE batch               [count][k+1][N]         (tlwe.jl:34-41)
+ *   MK LWE ciphertext batch  [count][p*n+1]          a[party][n] (mk_internals.jl:9), then b
+ *   MK extracted LWE batch   [count][p*N+1]
+ *   MK TLWE batch            [count][p+1][N]         a_1..a_p, b (mk_internals.jl:46-57)
+ *   MK BK, coefficient dom.  [p][n] samples (bk.key[j,i], mk_internals.jl:453-455), each
+ *                            x[l][p][N] | y[l][p][N] | c0[l][N] | c1[l][N]  (:240-250)
+ *   MK KSK                   [p] single-key KSKs    (mk_api.jl:66-71)
+ */
+#ifndef TFHE_B200_H
+#define TFHE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFHE_B200_OK 0
+#define TFHE_B200_EINVAL (-1)    /* bad argument / unsupported parameter set */
+#define TFHE_B200_ENODEV (-2)    /* no usable CUDA device */
+#define TFHE_B200_ECUDA (-3)     /* CUDA runtime error (see last_error) */
+#define TFHE_B200_ENOKEY (-4)    /* bootstrap / keyswitch key not loaded */
+#define TFHE_B200_ENOMEM (-5)
+
+/* SchemeParameters (api.jl:4-21), integer part; noise parameters never cross the ABI. */
+typedef struct {
+    int32_t n;        /* lwe_size */
+    int32_t N;        /* tlwe_polynomial_degree (must be 1024) */
+    int32_t k;        /* tlwe_mask_size (must be 1) */
+    int32_t l;        /* bs_decomp_length */
+    int32_t bgbit;    /* bs_log2_base */
+    int32_t t;        /* ks_decomp_length */
+    int32_t basebit;  /* ks_log2_base */
+    int32_t parties;  /* 1 = single-key context; 2..8 = MK-TFHE context (mk_api.jl:4-34) */
+} tfhe_b200_params;
+
+/* gate opcodes, in the order of gates.jl */
+enum {
+    TFHE_B200_NAND = 0,      /* gate_nand     gates.jl:15-18   */
+    TFHE_B200_OR = 1,        /* gate_or       gates.jl:27-30   */
+    TFHE_B200_AND = 2,       /* gate_and      gates.jl:39-42   */
+    TFHE_B200_XOR = 3,       /* gate_xor      gates.jl:51-54   */
+    TFHE_B200_XNOR = 4,      /* gate_xnor     gates.jl:63-66   */
+    TFHE_B200_NOT = 5,       /* gate_not      gates.jl:76-79   */
+    TFHE_B200_CONSTANT = 6,  /* gate_constant gates.jl:91-93   (x[g*(n+1)] != 0 selects true) */
+    TFHE_B200_NOR = 7,       /* gate_nor      gates.jl:102-105 */
+    TFHE_B200_ANDNY = 8,     /* gate_andny    gates.jl:114-117 */
+    TFHE_B200_ANDYN = 9,     /* gate_andyn    gates.jl:126-129 */
+    TFHE_B200_ORNY = 10,     /* gate_orny     gates.jl:138-141 */
+    TFHE_B200_ORYN = 11,     /* gate_oryn     gates.jl:150-153 */
+    TFHE_B200_MUX = 12       /* gate_mux      gates.jl:163-177 */
+};
+
+/* create flags */
+#define TFHE_B200_FLAG_SPLIT_FFT 0u    /* default: torus operand split in 16-bit halves; rounding bound proven */
+#define TFHE_B200_FLAG_UNSPLIT_FFT 1u  /* the reference's own precision regime (polynomials.jl:138-140): one 32-bit piece */
+
+typedef struct tfhe_b200_ctx tfhe_b200_ctx;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int tfhe_b200_device_count(void);
+/* One context = one parameter set + one key set on one GPU.  Replaces the role of CloudKey
+ * (api.jl:111-127) / MKCloudKey (mk_api.jl:85-101) as the holder of evaluation keys. */
+int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t flags, tfhe_b200_ctx** out);
+void tfhe_b200_destroy(tfhe_b200_ctx* ctx);
+/* ctx may be NULL: returns the last error of a failed create on this thread. */
+const char* tfhe_b200_last_error(const tfhe_b200_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches claim) */
+uint64_t tfhe_b200_kernel_launches(const tfhe_b200_ctx* ctx);
+int tfhe_b200_synchronize(tfhe_b200_ctx* ctx);
+
+/* ---- key loading (K6) -------------------------------------------------------------------- */
+/* BootstrapKey (bootstrap.jl:1-16): takes the int32 coefficient form and performs
+ * forward_transform.(bk) (bootstrap.jl:12 -> tgsw.jl:120-121) on the device. */
+int tfhe_b200_load_bk(tfhe_b200_ctx* ctx, const int32_t* bk);
+/* KeyswitchKey.key (keyswitch.jl:7-13,35-38) */
+int tfhe_b200_load_ksk(tfhe_b200_ctx* ctx, const int32_t* ksk);
+
+/* ---- single-key hot path, host buffers ---------------------------------------------------- */
+/* gate_* (gates.jl:15-177) over a batch; unused inputs may be NULL. */
+int tfhe_b200_gate_batch(tfhe_b200_ctx* ctx, int op, const int32_t* x, const int32_t* y, const int32_t* z,
+                         int32_t* out, size_t count);
+/* bootstrap (bootstrap.jl:92-95) */
+int tfhe_b200_bootstrap_batch(tfhe_b200_ctx* ctx, int32_t mu, const int32_t* x, int32_t* out, size_t count);
+/* bootstrap_wo_keyswitch (bootstrap.jl:69-82): out is [count][N*k+1] */
+int tfhe_b200_bootstrap_wo_ks_batch(tfhe_b200_ctx* ctx, int32_t mu, const int32_t* x, int32_t* out, size_t count);
+/* keyswitch (keyswitch.jl:45-80): in is [count][N*k+1] */
+int tfhe_b200_keyswitch_batch(tfhe_b200_ctx* ctx, const int32_t* in, int32_t* out, size_t count);
+/* tgsw_extern_mul (tgsw.jl:125-129): out[g] = BK[bk_index[g]] (x) acc[g]; acc/out [count][k+1][N] */
+int tfhe_b200_extern_product_batch(tfhe_b200_ctx* ctx, const int32_t* acc, const int32_t* bk_index,
+                                   int32_t* out, size_t count);
+/* blind_rotate (bootstrap.jl:32-39) on explicit accumulators: acc in/out [count][k+1][N],
+ * bara [count][n] already modulus-switched; only the first n_iter key elements are applied. */
+int tfhe_b200_blind_rotate_batch(tfhe_b200_ctx* ctx, const int32_t* acc_in, const int32_t* bara, int32_t n_iter,
+                                 int32_t* acc_out, size_t count);
+/* transformed_mul (polynomials.jl:142-144), exact for ANY int32 operands: x,y,out [count][N] */
+int tfhe_b200_polymul_batch(tfhe_b200_ctx* ctx, const int32_t* x, const int32_t* y, int32_t* out, size_t count);
+
+/* ---- single-key hot path, device buffers (asynchronous on `stream`) ------------------------ */
+int tfhe_b200_gate_batch_dev(tfhe_b200_ctx* ctx, int op, const int32_t* x, const int32_t* y, const int32_t* z,
+                             int32_t* out, size_t count, void* stream);
+int tfhe_b200_bootstrap_wo_ks_batch_dev(tfhe_b200_ctx* ctx, int32_t mu, const int32_t* x, int32_t* out,
+                                        size_t count, void* stream);
+int tfhe_b200_keyswitch_batch_dev(tfhe_b200_ctx* ctx, const int32_t* in, int32_t* out, size_t count, void* stream);
+
+/* ---- multi-key hot path (context created with params.parties >= 2) ------------------------- */
+/* MKBootstrapKey.key (mk_internals.jl:442-461), int32 coefficient form */
+int tfhe_b200_mk_load_bk(tfhe_b200_ctx* ctx, const int32_t* mk_bk);
+/* MKCloudKey.keyswitch_key (mk_api.jl:89,97): parties KSKs back to back */
+int tfhe_b200_mk_load_ksk(tfhe_b200_ctx* ctx, const int32_t* mk_ksk);
+/* mk_gate_nand (mk_gates.jl:7-12) */
+int tfhe_b200_mk_nand_batch(tfhe_b200_ctx* ctx, const int32_t* x, const int32_t* y, int32_t* out, size_t count);
+int tfhe_b200_mk_nand_batch_dev(tfhe_b200_ctx* ctx, const int32_t* x, const int32_t* y, int32_t* out, size_t count,
+                                void* stream);
+/* mk_bootstrap_wo_keyswitch (mk_internals.jl:498-509): out [count][p*N+1] */
+int tfhe_b200_mk_bootstrap_wo_ks_batch(tfhe_b200_ctx* ctx, int32_t mu, const int32_t* x, int32_t* out, size_t count);
+/* mk_keyswitch (mk_internals.jl:397-411): in [count][p*N+1] -> out [count][p*n+1] */
+int tfhe_b200_mk_keyswitch_batch(tfhe_b200_ctx* ctx, const int32_t* in, int32_t* out, size_t count);
+/* mk_tgsw_extern_mul (mk_internals.jl:348-391): out[g] = BK[party[g]][bk_index[g]] (x) acc[g]; acc/out [count][p+1][N] */
+int tfhe_b200_mk_extern_product_batch(tfhe_b200_ctx* ctx, const int32_t* acc, const int32_t* party,
+                                      const int32_t* bk_index, int32_t* out, size_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

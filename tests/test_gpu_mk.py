@@ -1,0 +1,83 @@
+"""GPU parity tests of the multi-key path (mk_internals.jl) through the C ABI."""
+import numpy as np
+import pytest
+
+import tfhe_jl_b200 as T
+from tfhe_jl_b200 import _cabi
+from conftest import random_torus
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+N = 1024
+
+
+def make_mk_ctx(mk, flags=_cabi.FLAG_SPLIT_FFT):
+    P = mk.params
+    ctx = T.Context(n=P.n, l=P.l, bgbit=P.bgbit, t=P.t, basebit=P.basebit, parties=mk.parties, flags=flags)
+    ctx.load_bk(mk.bk)
+    ctx.load_ksk(mk.ksk)
+    return ctx
+
+
+@pytest.mark.parametrize("p", [2, 4, 8])
+def test_mk_extern_product_matches_exact_oracle(p):
+    mk = O.mk_keygen(O.small_params(O.MK_PARAMS[p], 4), p, 40 + p)
+    octx = O.MKContext(mk)
+    ctx = make_mk_ctx(mk)
+    rng = np.random.default_rng(p)
+    cnt = 2 * p
+    acc = random_torus(rng, cnt, p + 1, N)
+    acc[0] = 0; acc[1] = -(2 ** 31)
+    party = (np.arange(cnt) % p).astype(np.int32)
+    idx = rng.integers(0, 4, cnt).astype(np.int32)
+    got = ctx.extern_product(acc, idx, party)
+    for g in range(cnt):
+        assert np.array_equal(got[g], octx.extern_mul(int(party[g]), int(idx[g]), acc[g], O.ROUTE_EXACT)), g
+
+
+def test_mk_nand_2party_full(mkkeys2, mkctx2):
+    """test/runtests.jl:60-100 on the GPU, ciphertext-identical to the oracle"""
+    ctx = make_mk_ctx(mkkeys2)
+    bits = np.random.default_rng(1).integers(0, 2, (10, 2)).astype(bool)
+    rng = O.Rng(2)
+    x, y = O.mk_encrypt(rng, mkkeys2, bits[:, 0]), O.mk_encrypt(rng, mkkeys2, bits[:, 1])
+    got = ctx.mk_nand(x, y)
+    assert np.array_equal(got, mkctx2.nand(x, y))
+    assert np.array_equal(O.mk_decrypt(mkkeys2, got), ~(bits[:, 0] & bits[:, 1]))
+    u = ctx.bootstrap_wo_ks(x[:2])
+    assert np.array_equal(u, mkctx2.bootstrap_wo_ks(x[:2]))
+    assert np.array_equal(ctx.keyswitch(u), mkctx2.keyswitch(u))
+
+
+def test_mk_unsplit_equals_split(mkkeys2):
+    a, b = make_mk_ctx(mkkeys2), make_mk_ctx(mkkeys2, _cabi.FLAG_UNSPLIT_FFT)
+    rng = O.Rng(3)
+    x, y = O.mk_encrypt(rng, mkkeys2, [True, False]), O.mk_encrypt(rng, mkkeys2, [True, True])
+    assert np.array_equal(a.mk_nand(x, y), b.mk_nand(x, y))
+
+
+@pytest.mark.parametrize("p", [4, 8])
+def test_mk_nand_small_key_4_and_8_parties(p):
+    """The 4- and 8-party sets (mk_api.jl:16-34) are never exercised by the reference's tests; a short
+    LWE key keeps the oracle fast while covering every code path."""
+    mk = O.mk_keygen(O.small_params(O.MK_PARAMS[p], 6), p, 50 + p)
+    octx = O.MKContext(mk)
+    ctx = make_mk_ctx(mk)
+    rng = O.Rng(p)
+    x, y = O.mk_encrypt(rng, mk, [True, False, True]), O.mk_encrypt(rng, mk, [True, True, False])
+    assert np.array_equal(ctx.mk_nand(x, y), octx.nand(x, y))
+
+
+def test_mk_api_mirror_2party():
+    """examples/multikey.jl through the mirrored API names, keys generated with GPU polymuls."""
+    rng = np.random.default_rng(5)
+    params = T.mktfhe_parameters_2party
+    sks = [T.SecretKey(rng, params) for _ in range(2)]
+    shared = T.SharedKey(rng, params)
+    parts = [T.CloudKeyPart(rng, sk, shared) for sk in sks]
+    ck = T.MKCloudKey(parts)
+    m1 = rng.integers(0, 2, 10).astype(bool); m2 = rng.integers(0, 2, 10).astype(bool)
+    e1, e2 = T.mk_encrypt(rng, sks, m1), T.mk_encrypt(rng, sks, m2)
+    assert np.array_equal(T.mk_decrypt(sks, e1), m1)
+    out = T.mk_gate_nand(ck, e1, e2)
+    assert np.array_equal(T.mk_decrypt(sks, out), ~(m1 & m2))

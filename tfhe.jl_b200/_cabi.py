@@ -1,0 +1,235 @@
+"""ctypes binding of libtfhe_b200.so — the same symbols a Julia ``ccall`` wrapper binds
+(include/tfhe_b200.h).  There is no fallback: if the CUDA library is missing or
+no GPU is present every compute call raises ``TFHEB200Error``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtfhe_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "tfhe_b200.h")
+
+OK, EINVAL, ENODEV, ECUDA, ENOKEY, ENOMEM = 0, -1, -2, -3, -4, -5
+FLAG_SPLIT_FFT, FLAG_UNSPLIT_FFT = 0, 1
+
+NAND, OR, AND, XOR, XNOR, NOT, CONSTANT, NOR, ANDNY, ANDYN, ORNY, ORYN, MUX = range(13)
+
+
+class TFHEB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"tfhe_b200 error {code}: {msg}")
+        self.code = code
+
+
+class CParams(C.Structure):
+    _fields_ = [(f, C.c_int32) for f in ("n", "N", "k", "l", "bgbit", "t", "basebit", "parties")]
+
+
+def build(force: bool = False) -> str:
+    """Compile the library in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+    csrc = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".inc"))] + [HEADER_PATH]
+    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        r = subprocess.run(["make", "-C", csrc] + (["-B"] if force else []), capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("building libtfhe_b200.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the C-ABI library (never builds implicitly: a missing library is an error)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TFHEB200Error(ENODEV, f"{LIB_PATH} not built (run __graft_entry__.build()); no CPU fallback exists")
+        L = C.CDLL(LIB_PATH)
+        i32p, vp, sz = C.c_void_p, C.c_void_p, C.c_size_t   # int32 pointers are passed as raw addresses
+        sig = {
+            "tfhe_b200_device_count": (C.c_int, []),
+            "tfhe_b200_create": (C.c_int, [C.POINTER(CParams), C.c_int, C.c_uint32, C.POINTER(vp)]),
+            "tfhe_b200_destroy": (None, [vp]),
+            "tfhe_b200_last_error": (C.c_char_p, [vp]),
+            "tfhe_b200_kernel_launches": (C.c_uint64, [vp]),
+            "tfhe_b200_synchronize": (C.c_int, [vp]),
+            "tfhe_b200_load_bk": (C.c_int, [vp, i32p]),
+            "tfhe_b200_load_ksk": (C.c_int, [vp, i32p]),
+            "tfhe_b200_gate_batch": (C.c_int, [vp, C.c_int, i32p, i32p, i32p, i32p, sz]),
+            "tfhe_b200_bootstrap_batch": (C.c_int, [vp, C.c_int32, i32p, i32p, sz]),
+            "tfhe_b200_bootstrap_wo_ks_batch": (C.c_int, [vp, C.c_int32, i32p, i32p, sz]),
+            "tfhe_b200_keyswitch_batch": (C.c_int, [vp, i32p, i32p, sz]),
+            "tfhe_b200_extern_product_batch": (C.c_int, [vp, i32p, i32p, i32p, sz]),
+            "tfhe_b200_blind_rotate_batch": (C.c_int, [vp, i32p, i32p, C.c_int32, i32p, sz]),
+            "tfhe_b200_polymul_batch": (C.c_int, [vp, i32p, i32p, i32p, sz]),
+            "tfhe_b200_gate_batch_dev": (C.c_int, [vp, C.c_int, i32p, i32p, i32p, i32p, sz, vp]),
+            "tfhe_b200_bootstrap_wo_ks_batch_dev": (C.c_int, [vp, C.c_int32, i32p, i32p, sz, vp]),
+            "tfhe_b200_keyswitch_batch_dev": (C.c_int, [vp, i32p, i32p, sz, vp]),
+            "tfhe_b200_mk_load_bk": (C.c_int, [vp, i32p]),
+            "tfhe_b200_mk_load_ksk": (C.c_int, [vp, i32p]),
+            "tfhe_b200_mk_nand_batch": (C.c_int, [vp, i32p, i32p, i32p, sz]),
+            "tfhe_b200_mk_nand_batch_dev": (C.c_int, [vp, i32p, i32p, i32p, sz, vp]),
+            "tfhe_b200_mk_bootstrap_wo_ks_batch": (C.c_int, [vp, C.c_int32, i32p, i32p, sz]),
+            "tfhe_b200_mk_keyswitch_batch": (C.c_int, [vp, i32p, i32p, sz]),
+            "tfhe_b200_mk_extern_product_batch": (C.c_int, [vp, i32p, i32p, i32p, i32p, sz]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        L._signatures = sig
+        _lib = L
+    return _lib
+
+
+def _host(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    if shape is not None:
+        assert a.shape == tuple(shape), (a.shape, shape)
+    return a
+
+
+def _addr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Context:
+    """One parameter set + one evaluation-key set on one GPU (CloudKey / MKCloudKey device side)."""
+
+    def __init__(self, n, N=1024, k=1, l=2, bgbit=10, t=8, basebit=2, parties=1, device=0, flags=FLAG_SPLIT_FFT):
+        self.n, self.N, self.k, self.l, self.bgbit, self.t, self.basebit, self.parties = n, N, k, l, bgbit, t, basebit, parties
+        self.device, self.flags = device, flags
+        self._h = C.c_void_p()
+        cp = CParams(n, N, k, l, bgbit, t, basebit, parties)
+        rc = lib().tfhe_b200_create(C.byref(cp), device, flags, C.byref(self._h))
+        if rc != 0:
+            raise TFHEB200Error(rc, (lib().tfhe_b200_last_error(None) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().tfhe_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise TFHEB200Error(rc, (lib().tfhe_b200_last_error(self._h) or b"").decode())
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(lib().tfhe_b200_kernel_launches(self._h))
+
+    def synchronize(self):
+        self._ck(lib().tfhe_b200_synchronize(self._h))
+
+    # widths
+    @property
+    def ct_words(self):
+        return self.parties * self.n + 1
+
+    @property
+    def ext_words(self):
+        return self.parties * self.N * self.k + 1
+
+    # ---- keys
+    def load_bk(self, bk):
+        if self.parties == 1:
+            bk = _host(bk).reshape(self.n, self.l, self.k + 1, self.k + 1, self.N)
+            self._ck(lib().tfhe_b200_load_bk(self._h, _addr(bk)))
+        else:
+            p = self.parties
+            bk = _host(bk).reshape(p, self.n, self.l * (2 * p + 2), self.N)
+            self._ck(lib().tfhe_b200_mk_load_bk(self._h, _addr(bk)))
+
+    def load_ksk(self, ksk):
+        shape = (self.N * self.k, self.t, (1 << self.basebit) - 1, self.n + 1)
+        if self.parties == 1:
+            ksk = _host(ksk).reshape(shape)
+            self._ck(lib().tfhe_b200_load_ksk(self._h, _addr(ksk)))
+        else:
+            ksk = _host(ksk).reshape((self.parties,) + shape)
+            self._ck(lib().tfhe_b200_mk_load_ksk(self._h, _addr(ksk)))
+
+    # ---- single-key, host buffers
+    def gate(self, op, x=None, y=None, z=None, count=None):
+        arrs = [None if a is None else np.atleast_2d(_host(a)) for a in (x, y, z)]
+        if count is None:
+            count = next(a.shape[0] for a in arrs if a is not None)
+        for a in arrs:
+            assert a is None or a.shape == (count, self.n + 1), a.shape
+        out = np.empty((count, self.n + 1), dtype=np.int32)
+        self._ck(lib().tfhe_b200_gate_batch(self._h, op, _addr(arrs[0]), _addr(arrs[1]), _addr(arrs[2]), _addr(out), count))
+        return out
+
+    def bootstrap(self, x, mu=1 << 29):
+        x = np.atleast_2d(_host(x)); out = np.empty_like(x)
+        self._ck(lib().tfhe_b200_bootstrap_batch(self._h, mu, _addr(x), _addr(out), x.shape[0]))
+        return out
+
+    def bootstrap_wo_ks(self, x, mu=1 << 29):
+        x = np.atleast_2d(_host(x)); out = np.empty((x.shape[0], self.ext_words), dtype=np.int32)
+        fn = lib().tfhe_b200_bootstrap_wo_ks_batch if self.parties == 1 else lib().tfhe_b200_mk_bootstrap_wo_ks_batch
+        self._ck(fn(self._h, mu, _addr(x), _addr(out), x.shape[0]))
+        return out
+
+    def keyswitch(self, u):
+        u = np.atleast_2d(_host(u)); out = np.empty((u.shape[0], self.ct_words), dtype=np.int32)
+        fn = lib().tfhe_b200_keyswitch_batch if self.parties == 1 else lib().tfhe_b200_mk_keyswitch_batch
+        self._ck(fn(self._h, _addr(u), _addr(out), u.shape[0]))
+        return out
+
+    def extern_product(self, acc, bk_index, party=None):
+        acc = _host(acc); count = acc.shape[0]; out = np.empty_like(acc)
+        idx = _host(np.broadcast_to(np.asarray(bk_index, dtype=np.int32), (count,)))
+        if self.parties == 1:
+            assert acc.shape == (count, self.k + 1, self.N)
+            self._ck(lib().tfhe_b200_extern_product_batch(self._h, _addr(acc), _addr(idx), _addr(out), count))
+        else:
+            assert acc.shape == (count, self.parties + 1, self.N)
+            par = _host(np.broadcast_to(np.asarray(party, dtype=np.int32), (count,)))
+            self._ck(lib().tfhe_b200_mk_extern_product_batch(self._h, _addr(acc), _addr(par), _addr(idx), _addr(out), count))
+        return out
+
+    def blind_rotate(self, acc, bara, n_iter=None):
+        acc = _host(acc); count = acc.shape[0]; out = np.empty_like(acc)
+        bara = _host(bara, (count, self.n))
+        n_iter = self.n if n_iter is None else n_iter
+        self._ck(lib().tfhe_b200_blind_rotate_batch(self._h, _addr(acc), _addr(bara), n_iter, _addr(out), count))
+        return out
+
+    def polymul(self, x, y):
+        x = np.atleast_2d(_host(x)); y = np.atleast_2d(_host(y)); out = np.empty_like(x)
+        assert x.shape == y.shape and x.shape[1] == self.N
+        self._ck(lib().tfhe_b200_polymul_batch(self._h, _addr(x), _addr(y), _addr(out), x.shape[0]))
+        return out
+
+    def mk_nand(self, x, y):
+        x = np.atleast_2d(_host(x)); y = np.atleast_2d(_host(y)); out = np.empty_like(x)
+        assert x.shape == y.shape and x.shape[1] == self.ct_words
+        self._ck(lib().tfhe_b200_mk_nand_batch(self._h, _addr(x), _addr(y), _addr(out), x.shape[0]))
+        return out
+
+    # ---- device buffers (raw addresses, e.g. torch ``tensor.data_ptr()``); asynchronous on ``stream``
+    def gate_dev(self, op, x_ptr, y_ptr, z_ptr, out_ptr, count, stream=0):
+        self._ck(lib().tfhe_b200_gate_batch_dev(self._h, op, x_ptr or None, y_ptr or None, z_ptr or None, out_ptr, count,
+                                                stream or None))
+
+    def bootstrap_wo_ks_dev(self, x_ptr, out_ptr, count, mu=1 << 29, stream=0):
+        self._ck(lib().tfhe_b200_bootstrap_wo_ks_batch_dev(self._h, mu, x_ptr, out_ptr, count, stream or None))
+
+    def keyswitch_dev(self, in_ptr, out_ptr, count, stream=0):
+        self._ck(lib().tfhe_b200_keyswitch_batch_dev(self._h, in_ptr, out_ptr, count, stream or None))
+
+    def mk_nand_dev(self, x_ptr, y_ptr, out_ptr, count, stream=0):
+        self._ck(lib().tfhe_b200_mk_nand_batch_dev(self._h, x_ptr, y_ptr, out_ptr, count, stream or None))
+
+
+def device_count() -> int:
+    return int(lib().tfhe_b200_device_count())

@@ -1,0 +1,512 @@
+// cabi.cu — host side of libtfhe_b200.so: the C ABI declared in include/tfhe_b200.h.
+// No CPU fallback exists in this file: every compute entry point launches the sm_100a kernels of
+// kernels.cuh / mk_kernels.cuh or fails with an error code.
+#include "../../include/tfhe_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "mk_kernels.cuh"
+
+using namespace tfhe_b200;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct tfhe_b200_ctx {
+    tfhe_b200_params P{};
+    int device = 0;
+    uint32_t flags = 0;
+    int NP = 2;
+    int occ = 3;                     // CTAs (of 2 gates) per SM the blind-rotation kernel is compiled for
+    cudaStream_t stream = nullptr;   // used by the host-buffer entry points
+    double2* d_E = nullptr;          // exp(-i*pi*x/1024), x < 2048
+    double2* d_bk_fft = nullptr;     // single-key: [n][l][2][2][NP][512]; MK: [p][n][l*(2p+2)][NP][512]
+    int32_t* d_ksk = nullptr;        // [parties][Nk][t][base-1][stride]
+    int ksk_stride = 0;
+    bool have_bk = false, have_ksk = false;
+    DevBuf bx, by, bz, bout, bu1, bu2, bidx, bidx2;
+    std::mutex mu;
+    std::string err;
+    std::atomic<uint64_t> launches{0};
+    size_t chunk = 1 << 16;          // gates per host-staged chunk
+};
+
+namespace {
+
+int fail(tfhe_b200_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(ctx, TFHE_B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+int reserve(tfhe_b200_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (b.cap >= bytes) return 0;
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    CU(cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+    return 0;
+}
+
+bool single_key_supported(int l, int bgbit) { return (l == 2 && bgbit == 10) || (l == 3 && bgbit == 7); }
+bool mk_supported(int p, int l, int bgbit) {
+    return (p >= 2 && p <= 8) && ((l == 4 && bgbit == 7) || (l == 5 && bgbit == 6) || (l == 8 && bgbit == 4));
+}
+
+int env_int(const char* name, int dflt) {
+    const char* s = std::getenv(name);
+    return s && *s ? std::atoi(s) : dflt;
+}
+
+// ---- kernel dispatch ------------------------------------------------------------------------------
+template <int L, int BGBIT, int NP, int G, int MB, int MODE>
+int launch_br_g(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
+    auto kern = blind_rotate_kernel<L, BGBIT, NP, G, MB, MODE>;
+    size_t smem = (size_t)G * (kGroupSmemBytes + A.n_pad * 4);
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned grid = (unsigned)((A.count + G - 1) / G);
+    kern<<<grid, 64 * G, smem, s>>>(A);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+// G = gates per CTA, MB = CTAs per SM the register allocation is tuned for (TFHE_B200_OCC)
+template <int L, int BGBIT, int NP, int MODE>
+int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
+    if (MODE == 1) return launch_br_g<L, BGBIT, NP, 2, 2, MODE>(ctx, A, s);
+    switch (ctx->occ) {
+        case 2: return launch_br_g<L, BGBIT, NP, 2, 2, MODE>(ctx, A, s);
+        case 4: return launch_br_g<L, BGBIT, NP, 2, 4, MODE>(ctx, A, s);
+        default: return launch_br_g<L, BGBIT, NP, 2, 3, MODE>(ctx, A, s);
+    }
+}
+template <int MODE>
+int launch_br(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
+    const int l = ctx->P.l, bg = ctx->P.bgbit;
+    if (A.count == 0) return 0;
+    if (l == 2 && bg == 10) return ctx->NP == 2 ? launch_br_np<2, 10, 2, MODE>(ctx, A, s) : launch_br_np<2, 10, 1, MODE>(ctx, A, s);
+    if (l == 3 && bg == 7) return ctx->NP == 2 ? launch_br_np<3, 7, 2, MODE>(ctx, A, s) : launch_br_np<3, 7, 1, MODE>(ctx, A, s);
+    return fail(ctx, TFHE_B200_EINVAL, "unsupported (l, bgbit)");
+}
+
+int launch_extern(tfhe_b200_ctx* ctx, const int32_t* acc, const int32_t* idx, int32_t* out, size_t count, cudaStream_t s) {
+    const int l = ctx->P.l, bg = ctx->P.bgbit;
+    if (count == 0) return 0;
+    unsigned grid = (unsigned)count;
+    if (l == 2 && bg == 10) {
+        if (ctx->NP == 2) extern_product_kernel<2, 10, 2><<<grid, 64, 0, s>>>(ctx->d_bk_fft, ctx->d_E, acc, idx, out);
+        else extern_product_kernel<2, 10, 1><<<grid, 64, 0, s>>>(ctx->d_bk_fft, ctx->d_E, acc, idx, out);
+    } else if (l == 3 && bg == 7) {
+        if (ctx->NP == 2) extern_product_kernel<3, 7, 2><<<grid, 64, 0, s>>>(ctx->d_bk_fft, ctx->d_E, acc, idx, out);
+        else extern_product_kernel<3, 7, 1><<<grid, 64, 0, s>>>(ctx->d_bk_fft, ctx->d_E, acc, idx, out);
+    } else return fail(ctx, TFHE_B200_EINVAL, "unsupported (l, bgbit)");
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+// keyswitch of ciphertexts [count][Nk+1] -> [count][n+1] with key set `party`
+int launch_keyswitch(tfhe_b200_ctx* ctx, const int32_t* in, int32_t* out, size_t count, cudaStream_t s) {
+    if (count == 0) return 0;
+    const auto& P = ctx->P;
+    KeyswitchArgs A{};
+    A.ksk = ctx->d_ksk; A.in = in; A.out = out; A.out_b = out;
+    A.n = P.n; A.Nk = P.N * P.k; A.t = P.t; A.basebit = P.basebit; A.stride = ctx->ksk_stride;
+    A.in_stride = A.Nk + 1; A.in_offset = 0; A.in_b_offset = A.Nk;
+    A.out_stride = P.n + 1; A.out_offset = 0; A.b_offset = P.n; A.b_mode = 0;
+    keyswitch_kernel<<<(unsigned)count, ctx->ksk_stride / 4, A.Nk * sizeof(int32_t), s>>>(A);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+int launch_lincomb(tfhe_b200_ctx* ctx, const int32_t* x, const int32_t* y, int32_t* out, int32_t ka, int32_t kb,
+                   int32_t cb, int width, size_t rows, int const_mode, cudaStream_t s) {
+    if (rows == 0) return 0;
+    unsigned long long total = (unsigned long long)rows * width;
+    unsigned grid = (unsigned)((total + 255) / 256);
+    lincomb_kernel<<<grid, 256, 0, s>>>(x, y, out, ka, kb, cb, width, total, const_mode);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+constexpr int32_t kMu8 = 1 << 29;    // encode_message(1, 8)   numeric-functions.jl:42-45
+constexpr int32_t kMu4 = 1 << 30;    // encode_message(1, 4)
+
+// prologue coefficients of the ten bootstrapped binary gates (gates.jl)
+bool gate_coeffs(int op, int32_t& cb, int32_t& ka, int32_t& kb) {
+    switch (op) {
+        case TFHE_B200_NAND:  cb = kMu8;  ka = -1; kb = -1; return true;
+        case TFHE_B200_OR:    cb = kMu8;  ka = 1;  kb = 1;  return true;
+        case TFHE_B200_AND:   cb = -kMu8; ka = 1;  kb = 1;  return true;
+        case TFHE_B200_XOR:   cb = kMu4;  ka = 2;  kb = 2;  return true;
+        case TFHE_B200_XNOR:  cb = -kMu4; ka = -2; kb = -2; return true;
+        case TFHE_B200_NOR:   cb = -kMu8; ka = -1; kb = -1; return true;
+        case TFHE_B200_ANDNY: cb = -kMu8; ka = -1; kb = 1;  return true;
+        case TFHE_B200_ANDYN: cb = -kMu8; ka = 1;  kb = -1; return true;
+        case TFHE_B200_ORNY:  cb = kMu8;  ka = -1; kb = 1;  return true;
+        case TFHE_B200_ORYN:  cb = kMu8;  ka = 1;  kb = -1; return true;
+        default: return false;
+    }
+}
+
+BlindRotateArgs br_args(tfhe_b200_ctx* ctx, size_t count) {
+    BlindRotateArgs A{};
+    A.bk_fft = ctx->d_bk_fft; A.E = ctx->d_E;
+    A.n = ctx->P.n; A.n_iter = ctx->P.n; A.n_pad = (ctx->P.n + 3) & ~3;
+    A.count = count; A.mu = kMu8;
+    return A;
+}
+
+int check_single(tfhe_b200_ctx* ctx, bool need_bk, bool need_ksk) {
+    if (!ctx) return TFHE_B200_EINVAL;
+    if (ctx->P.parties != 1) return fail(ctx, TFHE_B200_EINVAL, "single-key entry point called on an MK context");
+    if (need_bk && !ctx->have_bk) return fail(ctx, TFHE_B200_ENOKEY, "bootstrap key not loaded");
+    if (need_ksk && !ctx->have_ksk) return fail(ctx, TFHE_B200_ENOKEY, "keyswitch key not loaded");
+    CU(cudaSetDevice(ctx->device));
+    return 0;
+}
+
+// bootstrap_wo_keyswitch with fused prologue, device pointers
+int bootstrap_wo_ks_dev(tfhe_b200_ctx* ctx, const int32_t* x, const int32_t* y, int32_t ka, int32_t kb, int32_t cb,
+                        int32_t mu, int32_t* out, size_t count, cudaStream_t s) {
+    BlindRotateArgs A = br_args(ctx, count);
+    A.x = x; A.y = y; A.ka = ka; A.kb = kb; A.cb = cb; A.mu = mu; A.out = out;
+    return launch_br<0>(ctx, A, s);
+}
+
+// one gate over device-resident ciphertexts; u1/u2 are scratch [count][Nk+1]
+int gate_dev(tfhe_b200_ctx* ctx, int op, const int32_t* x, const int32_t* y, const int32_t* z, int32_t* out,
+             size_t count, int32_t* u1, int32_t* u2, cudaStream_t s) {
+    const int w = ctx->P.n + 1, wu = ctx->P.N * ctx->P.k + 1;
+    int32_t cb, ka, kb;
+    int rc;
+    if (gate_coeffs(op, cb, ka, kb)) {
+        if (!x || !y) return fail(ctx, TFHE_B200_EINVAL, "binary gate needs x and y");
+        if ((rc = bootstrap_wo_ks_dev(ctx, x, y, ka, kb, cb, kMu8, u1, count, s))) return rc;   // bootstrap.jl:93
+        return launch_keyswitch(ctx, u1, out, count, s);                                        // bootstrap.jl:94
+    }
+    switch (op) {
+        case TFHE_B200_NOT:
+            if (!x) return fail(ctx, TFHE_B200_EINVAL, "NOT needs x");
+            return launch_lincomb(ctx, x, nullptr, out, -1, 0, 0, w, count, 0, s);
+        case TFHE_B200_CONSTANT:
+            if (!x) return fail(ctx, TFHE_B200_EINVAL, "CONSTANT needs x (value flags)");
+            return launch_lincomb(ctx, x, nullptr, out, 0, 0, kMu8, w, count, 1, s);
+        case TFHE_B200_MUX:
+            if (!x || !y || !z) return fail(ctx, TFHE_B200_EINVAL, "MUX needs x, y and z");
+            if ((rc = bootstrap_wo_ks_dev(ctx, x, y, 1, 1, -kMu8, kMu8, u1, count, s))) return rc;    // gates.jl:166-167
+            if ((rc = bootstrap_wo_ks_dev(ctx, x, z, -1, 1, -kMu8, kMu8, u2, count, s))) return rc;   // gates.jl:170-171
+            if ((rc = launch_lincomb(ctx, u1, u2, u1, 1, 1, kMu8, wu, count, 0, s))) return rc;       // gates.jl:174
+            return launch_keyswitch(ctx, u1, out, count, s);                                          // gates.jl:176
+        default:
+            return fail(ctx, TFHE_B200_EINVAL, "unknown gate opcode");
+    }
+}
+
+}  // namespace
+
+// =====================================================================================================
+// All functions below were declared extern "C" by include/tfhe_b200.h and keep that linkage.
+
+int tfhe_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t flags, tfhe_b200_ctx** out) {
+    tfhe_b200_ctx* ctx = nullptr;   // for the CU macro: errors go to the thread-local string
+    if (!params || !out) return fail(nullptr, TFHE_B200_EINVAL, "null argument");
+    *out = nullptr;
+    const auto& P = *params;
+    if (P.N != 1024 || P.k != 1) return fail(nullptr, TFHE_B200_EINVAL, "only N = 1024, k = 1 are supported");
+    if (P.n < 1 || P.n > 4096) return fail(nullptr, TFHE_B200_EINVAL, "n out of range");
+    if (P.t < 1 || P.basebit < 1 || P.t * P.basebit > 31 || P.basebit > 4) return fail(nullptr, TFHE_B200_EINVAL, "bad keyswitch parameters");
+    if (P.parties == 1 ? !single_key_supported(P.l, P.bgbit) : !mk_supported(P.parties, P.l, P.bgbit))
+        return fail(nullptr, TFHE_B200_EINVAL, "unsupported (parties, l, bgbit): supported are the reference's parameter sets");
+    if (tfhe_b200_device_count() <= device_id || device_id < 0)
+        return fail(nullptr, TFHE_B200_ENODEV, "no CUDA device " + std::to_string(device_id) + " (this library has no CPU fallback)");
+    CU(cudaSetDevice(device_id));
+    tfhe_b200_ctx* c = new tfhe_b200_ctx();
+    c->P = P; c->device = device_id; c->flags = flags;
+    c->NP = (flags & TFHE_B200_FLAG_UNSPLIT_FFT) ? 1 : 2;
+    c->occ = env_int("TFHE_B200_OCC", 3);
+    c->chunk = (size_t)env_int("TFHE_B200_CHUNK", 1 << 16);
+    ctx = c;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return fail(nullptr, TFHE_B200_ECUDA, cudaGetErrorString(e)); }
+    // twiddle table E[x] = exp(-i*pi*x/1024), computed in long double
+    std::vector<double2> E(2048);
+    for (int x = 0; x < 2048; x++) {
+        long double a = -3.14159265358979323846264338327950288L * (long double)x / 1024.0L;
+        E[x] = make_double2((double)cosl(a), (double)sinl(a));
+    }
+    e = cudaMalloc(&c->d_E, sizeof(double2) * 2048);
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_E, E.data(), sizeof(double2) * 2048, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { tfhe_b200_destroy(c); return fail(nullptr, TFHE_B200_ECUDA, cudaGetErrorString(e)); }
+    *out = c;
+    return 0;
+}
+
+void tfhe_b200_destroy(tfhe_b200_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    for (DevBuf* b : {&c->bx, &c->by, &c->bz, &c->bout, &c->bu1, &c->bu2, &c->bidx, &c->bidx2})
+        if (b->p) cudaFree(b->p);
+    if (c->d_E) cudaFree(c->d_E);
+    if (c->d_bk_fft) cudaFree(c->d_bk_fft);
+    if (c->d_ksk) cudaFree(c->d_ksk);
+    delete c;
+}
+
+const char* tfhe_b200_last_error(const tfhe_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+uint64_t tfhe_b200_kernel_launches(const tfhe_b200_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+int tfhe_b200_synchronize(tfhe_b200_ctx* ctx) {
+    if (!ctx) return TFHE_B200_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    return 0;
+}
+
+// ---- key loading ------------------------------------------------------------------------------------
+static int load_bk_polys(tfhe_b200_ctx* ctx, const int32_t* bk, size_t polys) {
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->d_bk_fft) { CU(cudaFree(ctx->d_bk_fft)); ctx->d_bk_fft = nullptr; }
+    CU(cudaMalloc(&ctx->d_bk_fft, polys * ctx->NP * kSpectrum * sizeof(double2)));
+    // transform in slabs so the int32 staging buffer stays small
+    const size_t slab = 1 << 14;
+    int32_t* d_tmp = nullptr;
+    CU(cudaMalloc(&d_tmp, std::min(slab, polys) * kN * sizeof(int32_t)));
+    for (size_t off = 0; off < polys; off += slab) {
+        size_t cnt = std::min(slab, polys - off);
+        cudaError_t e = cudaMemcpyAsync(d_tmp, bk + off * kN, cnt * kN * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) {
+            double2* o = ctx->d_bk_fft + off * ctx->NP * kSpectrum;
+            if (ctx->NP == 2) bk_transform_kernel<2><<<(unsigned)cnt, 64, 0, ctx->stream>>>(d_tmp, o, ctx->d_E);
+            else bk_transform_kernel<1><<<(unsigned)cnt, 64, 0, ctx->stream>>>(d_tmp, o, ctx->d_E);
+            e = cudaGetLastError();
+            ctx->launches++;
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { cudaFree(d_tmp); return fail(ctx, TFHE_B200_ECUDA, cudaGetErrorString(e)); }
+    }
+    CU(cudaFree(d_tmp));
+    ctx->have_bk = true;
+    return 0;
+}
+
+int tfhe_b200_load_bk(tfhe_b200_ctx* ctx, const int32_t* bk) {
+    if (!ctx || !bk) return TFHE_B200_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->P.parties != 1) return fail(ctx, TFHE_B200_EINVAL, "use tfhe_b200_mk_load_bk on an MK context");
+    return load_bk_polys(ctx, bk, (size_t)ctx->P.n * ctx->P.l * 4);
+}
+
+static int load_ksk_sets(tfhe_b200_ctx* ctx, const int32_t* ksk, int sets) {
+    const auto& P = ctx->P;
+    CU(cudaSetDevice(ctx->device));
+    const size_t rows = (size_t)sets * P.N * P.k * P.t * ((1 << P.basebit) - 1);
+    const int stride = (P.n + 1 + 31) & ~31;
+    if (ctx->d_ksk) { CU(cudaFree(ctx->d_ksk)); ctx->d_ksk = nullptr; }
+    CU(cudaMalloc(&ctx->d_ksk, rows * stride * sizeof(int32_t)));
+    CU(cudaMemsetAsync(ctx->d_ksk, 0, rows * stride * sizeof(int32_t), ctx->stream));
+    CU(cudaMemcpy2DAsync(ctx->d_ksk, stride * sizeof(int32_t), ksk, (P.n + 1) * sizeof(int32_t),
+                         (P.n + 1) * sizeof(int32_t), rows, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->ksk_stride = stride;
+    ctx->have_ksk = true;
+    return 0;
+}
+
+int tfhe_b200_load_ksk(tfhe_b200_ctx* ctx, const int32_t* ksk) {
+    if (!ctx || !ksk) return TFHE_B200_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->P.parties != 1) return fail(ctx, TFHE_B200_EINVAL, "use tfhe_b200_mk_load_ksk on an MK context");
+    return load_ksk_sets(ctx, ksk, 1);
+}
+
+// ---- single-key, device buffers ---------------------------------------------------------------------
+int tfhe_b200_gate_batch_dev(tfhe_b200_ctx* ctx, int op, const int32_t* x, const int32_t* y, const int32_t* z,
+                             int32_t* out, size_t count, void* stream) {
+    int rc = check_single(ctx, true, true);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t wu = (size_t)ctx->P.N * ctx->P.k + 1;
+    if ((rc = reserve(ctx, ctx->bu1, count * wu * 4))) return rc;
+    if (op == TFHE_B200_MUX && (rc = reserve(ctx, ctx->bu2, count * wu * 4))) return rc;
+    return gate_dev(ctx, op, x, y, z, out, count, (int32_t*)ctx->bu1.p, (int32_t*)ctx->bu2.p, (cudaStream_t)stream);
+}
+
+int tfhe_b200_bootstrap_wo_ks_batch_dev(tfhe_b200_ctx* ctx, int32_t mu, const int32_t* x, int32_t* out, size_t count,
+                                        void* stream) {
+    int rc = check_single(ctx, true, false);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return bootstrap_wo_ks_dev(ctx, x, nullptr, 1, 0, 0, mu, out, count, (cudaStream_t)stream);
+}
+
+int tfhe_b200_keyswitch_batch_dev(tfhe_b200_ctx* ctx, const int32_t* in, int32_t* out, size_t count, void* stream) {
+    int rc = check_single(ctx, false, true);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return launch_keyswitch(ctx, in, out, count, (cudaStream_t)stream);
+}
+
+// ---- single-key, host buffers -----------------------------------------------------------------------
+// Generic chunked host driver: up to three inputs of widths win, one output of width wout.
+template <typename F>
+static int host_chunks(tfhe_b200_ctx* ctx, const int32_t* const hin[3], const size_t win[3], int32_t* hout, size_t wout,
+                       size_t count, F&& body) {
+    DevBuf* bin[3] = {&ctx->bx, &ctx->by, &ctx->bz};
+    for (size_t off = 0; off < count; off += ctx->chunk) {
+        size_t cnt = std::min(ctx->chunk, count - off);
+        int rc;
+        int32_t* din[3] = {nullptr, nullptr, nullptr};
+        for (int a = 0; a < 3; a++) {
+            if (!hin[a]) continue;
+            if ((rc = reserve(ctx, *bin[a], cnt * win[a] * 4))) return rc;
+            din[a] = (int32_t*)bin[a]->p;
+            CU(cudaMemcpyAsync(din[a], hin[a] + off * win[a], cnt * win[a] * 4, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        if ((rc = reserve(ctx, ctx->bout, cnt * wout * 4))) return rc;
+        if ((rc = body(din[0], din[1], din[2], (int32_t*)ctx->bout.p, cnt))) return rc;
+        CU(cudaMemcpyAsync(hout + off * wout, ctx->bout.p, cnt * wout * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+int tfhe_b200_gate_batch(tfhe_b200_ctx* ctx, int op, const int32_t* x, const int32_t* y, const int32_t* z,
+                         int32_t* out, size_t count) {
+    int rc = check_single(ctx, true, true);
+    if (rc) return rc;
+    if (!out) return fail(ctx, TFHE_B200_EINVAL, "null output");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t w = (size_t)ctx->P.n + 1, wu = (size_t)ctx->P.N * ctx->P.k + 1;
+    const int32_t* hin[3] = {x, y, z};
+    const size_t win[3] = {w, w, w};
+    return host_chunks(ctx, hin, win, out, w, count, [&](int32_t* dx, int32_t* dy, int32_t* dz, int32_t* dout, size_t cnt) {
+        int r;
+        if ((r = reserve(ctx, ctx->bu1, cnt * wu * 4))) return r;
+        if (op == TFHE_B200_MUX && (r = reserve(ctx, ctx->bu2, cnt * wu * 4))) return r;
+        return gate_dev(ctx, op, dx, dy, dz, dout, cnt, (int32_t*)ctx->bu1.p, (int32_t*)ctx->bu2.p, ctx->stream);
+    });
+}
+
+int tfhe_b200_bootstrap_wo_ks_batch(tfhe_b200_ctx* ctx, int32_t mu, const int32_t* x, int32_t* out, size_t count) {
+    int rc = check_single(ctx, true, false);
+    if (rc) return rc;
+    if (!x || !out) return fail(ctx, TFHE_B200_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t w = (size_t)ctx->P.n + 1, wu = (size_t)ctx->P.N * ctx->P.k + 1;
+    const int32_t* hin[3] = {x, nullptr, nullptr};
+    const size_t win[3] = {w, 0, 0};
+    return host_chunks(ctx, hin, win, out, wu, count, [&](int32_t* dx, int32_t*, int32_t*, int32_t* dout, size_t cnt) {
+        return bootstrap_wo_ks_dev(ctx, dx, nullptr, 1, 0, 0, mu, dout, cnt, ctx->stream);
+    });
+}
+
+int tfhe_b200_keyswitch_batch(tfhe_b200_ctx* ctx, const int32_t* in, int32_t* out, size_t count) {
+    int rc = check_single(ctx, false, true);
+    if (rc) return rc;
+    if (!in || !out) return fail(ctx, TFHE_B200_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t w = (size_t)ctx->P.n + 1, wu = (size_t)ctx->P.N * ctx->P.k + 1;
+    const int32_t* hin[3] = {in, nullptr, nullptr};
+    const size_t win[3] = {wu, 0, 0};
+    return host_chunks(ctx, hin, win, out, w, count, [&](int32_t* din, int32_t*, int32_t*, int32_t* dout, size_t cnt) {
+        return launch_keyswitch(ctx, din, dout, cnt, ctx->stream);
+    });
+}
+
+int tfhe_b200_bootstrap_batch(tfhe_b200_ctx* ctx, int32_t mu, const int32_t* x, int32_t* out, size_t count) {
+    int rc = check_single(ctx, true, true);
+    if (rc) return rc;
+    if (!x || !out) return fail(ctx, TFHE_B200_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t w = (size_t)ctx->P.n + 1, wu = (size_t)ctx->P.N * ctx->P.k + 1;
+    const int32_t* hin[3] = {x, nullptr, nullptr};
+    const size_t win[3] = {w, 0, 0};
+    return host_chunks(ctx, hin, win, out, w, count, [&](int32_t* dx, int32_t*, int32_t*, int32_t* dout, size_t cnt) {
+        int r;
+        if ((r = reserve(ctx, ctx->bu1, cnt * wu * 4))) return r;
+        if ((r = bootstrap_wo_ks_dev(ctx, dx, nullptr, 1, 0, 0, mu, (int32_t*)ctx->bu1.p, cnt, ctx->stream))) return r;
+        return launch_keyswitch(ctx, (int32_t*)ctx->bu1.p, dout, cnt, ctx->stream);
+    });
+}
+
+int tfhe_b200_extern_product_batch(tfhe_b200_ctx* ctx, const int32_t* acc, const int32_t* bk_index, int32_t* out,
+                                   size_t count) {
+    int rc = check_single(ctx, true, false);
+    if (rc) return rc;
+    if (!acc || !bk_index || !out) return fail(ctx, TFHE_B200_EINVAL, "null argument");
+    for (size_t g = 0; g < count; g++)
+        if (bk_index[g] < 0 || bk_index[g] >= ctx->P.n) return fail(ctx, TFHE_B200_EINVAL, "bk_index out of range");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const int32_t* hin[3] = {acc, bk_index, nullptr};
+    const size_t win[3] = {2 * (size_t)kN, 1, 0};
+    return host_chunks(ctx, hin, win, out, 2 * (size_t)kN, count, [&](int32_t* dacc, int32_t* didx, int32_t*, int32_t* dout, size_t cnt) {
+        return launch_extern(ctx, dacc, didx, dout, cnt, ctx->stream);
+    });
+}
+
+int tfhe_b200_blind_rotate_batch(tfhe_b200_ctx* ctx, const int32_t* acc_in, const int32_t* bara, int32_t n_iter,
+                                 int32_t* acc_out, size_t count) {
+    int rc = check_single(ctx, true, false);
+    if (rc) return rc;
+    if (!acc_in || !bara || !acc_out) return fail(ctx, TFHE_B200_EINVAL, "null argument");
+    if (n_iter < 0 || n_iter > ctx->P.n) return fail(ctx, TFHE_B200_EINVAL, "n_iter out of range");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const int32_t* hin[3] = {acc_in, bara, nullptr};
+    const size_t win[3] = {2 * (size_t)kN, (size_t)ctx->P.n, 0};
+    return host_chunks(ctx, hin, win, acc_out, 2 * (size_t)kN, count, [&](int32_t* dacc, int32_t* dbara, int32_t*, int32_t* dout, size_t cnt) {
+        BlindRotateArgs A = br_args(ctx, cnt);
+        A.acc_in = dacc; A.bara_in = dbara; A.n_iter = n_iter; A.out = dout;
+        return launch_br<1>(ctx, A, ctx->stream);
+    });
+}
+
+int tfhe_b200_polymul_batch(tfhe_b200_ctx* ctx, const int32_t* x, const int32_t* y, int32_t* out, size_t count) {
+    if (!ctx) return TFHE_B200_EINVAL;
+    if (!x || !y || !out) return fail(ctx, TFHE_B200_EINVAL, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const int32_t* hin[3] = {x, y, nullptr};
+    const size_t win[3] = {(size_t)kN, (size_t)kN, 0};
+    return host_chunks(ctx, hin, win, out, (size_t)kN, count, [&](int32_t* dx, int32_t* dy, int32_t*, int32_t* dout, size_t cnt) {
+        polymul_kernel<<<(unsigned)cnt, 64, 0, ctx->stream>>>(dx, dy, dout, ctx->d_E);
+        CU(cudaGetLastError());
+        ctx->launches++;
+        return 0;
+    });
+}
+
+#include "mk_cabi.inc"

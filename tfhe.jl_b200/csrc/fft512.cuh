@@ -1,0 +1,176 @@
+// fft512.cuh — negacyclic transform of degree-1024 real polynomials for sm_100a.
+//
+// Replaces forward_transform / inverse_transform of the reference (polynomials.jl:106-132), which
+// call FFTW on a folded N/2-point complex-double buffer.  Same mathematics, own dataflow:
+//
+//   p(X) mod (X^1024 + 1), real coefficients  ->  z_j = p_j - i*p_{j+512}   (= p mod X^512 + i)
+//   Z_k = z(zeta^(4k+1)),  zeta = exp(-i*pi/1024),  k = 0..511              (roots of X^512 = -i)
+//
+// A 64-thread group owns one transform; every thread keeps 8 complex points in registers and the
+// transform is three radix-8 passes with two exchanges through shared memory:
+//
+//   pass 1: thread t holds j = t + 64m (m = 0..7).  The twist exp(-i*pi*j/1024) is factored as
+//           exp(-i*pi*t/1024) * exp(-i*pi*m/16): the second factor is a compile-time constant applied
+//           before the radix-8 butterfly, the first is merged with the pass-1 twiddle into
+//           T_q(t) = E(t*(4q+1)), E(x) = exp(-i*pi*x/1024).
+//   exchange 1 (X1): (t1,t2 | q) -> thread t1 + 8q, register t2          [t = t1 + 8*t2]
+//   pass 2: radix-8 over t2 -> q2, twiddle W64^(t1*q2) = E(32*t1*q2)
+//   exchange 2 (X2): (t1,q | q2) -> thread q2 + 8q, register t1          [XOR swizzle, conflict-free]
+//   pass 3: radix-8 over t1 -> q3
+//
+// Output: thread v = q2 + 8q, register q3 holds frequency k = q + 8*q2 + 64*q3.  The transform-domain
+// layout of every stored spectrum is therefore [q3][v] (8 x 64 complex), which makes the pointwise
+// multiply-accumulate a perfectly coalesced 16-byte load per thread, and the inverse transform is the
+// exact mirror (no reordering pass anywhere).
+//
+// Both exchanges use 16-byte (double2) shared-memory accesses; a quarter-warp always touches 8
+// distinct 16-byte bank groups, so all LDS.128/STS.128 are conflict-free.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tfhe_b200 {
+
+constexpr int kN = 1024;          // polynomial degree (all parameter sets of the reference use 1024)
+constexpr int kHalf = 512;        // complex points per transform
+constexpr int kGroup = 64;        // threads per transform
+constexpr int kSpectrum = 512;    // double2 per stored spectrum
+
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) {
+    return make_double2(fma(a.x, b.x, -(a.y * b.y)), fma(a.x, b.y, a.y * b.x));
+}
+// a * conj(b)
+__device__ __forceinline__ double2 cmulc(double2 a, double2 b) {
+    return make_double2(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -(a.x * b.y)));
+}
+// acc += a * b
+__device__ __forceinline__ void cmac(double2& acc, double2 a, double2 b) {
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+template <bool INV> __device__ __forceinline__ double2 tw(double2 a, double2 w) { return INV ? cmulc(a, w) : cmul(a, w); }
+// multiply by -i (forward) or +i (inverse)
+template <bool INV> __device__ __forceinline__ double2 rot90(double2 a) {
+    return INV ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x);
+}
+
+// 64-thread group barrier (barrier 0 is left to __syncthreads)
+__device__ __forceinline__ void group_sync(int bar_id) {
+    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+}
+
+// 8-point DFT in registers, natural order in and out.  Forward kernel exp(-2*pi*i*m*q/8); INV conjugates.
+template <bool INV> __device__ __forceinline__ void dft8(double2 (&a)[8]) {
+    constexpr double h = 0.70710678118654752440;
+    double2 s0 = cadd(a[0], a[4]), d0 = csub(a[0], a[4]);
+    double2 s1 = cadd(a[1], a[5]), d1 = csub(a[1], a[5]);
+    double2 s2 = cadd(a[2], a[6]), d2 = csub(a[2], a[6]);
+    double2 s3 = cadd(a[3], a[7]), d3 = csub(a[3], a[7]);
+    // d_m *= W8^m
+    if (!INV) {
+        d1 = make_double2((d1.x + d1.y) * h, (d1.y - d1.x) * h);
+        d3 = make_double2((d3.y - d3.x) * h, -(d3.x + d3.y) * h);
+    } else {
+        d1 = make_double2((d1.x - d1.y) * h, (d1.x + d1.y) * h);
+        d3 = make_double2(-(d3.x + d3.y) * h, (d3.x - d3.y) * h);
+    }
+    d2 = rot90<INV>(d2);
+    double2 e0 = cadd(s0, s2), e1 = csub(s0, s2), o0 = cadd(s1, s3), o1 = rot90<INV>(csub(s1, s3));
+    double2 f0 = cadd(d0, d2), f1 = csub(d0, d2), g0 = cadd(d1, d3), g1 = rot90<INV>(csub(d1, d3));
+    a[0] = cadd(e0, o0); a[4] = csub(e0, o0); a[2] = cadd(e1, o1); a[6] = csub(e1, o1);
+    a[1] = cadd(f0, g0); a[5] = csub(f0, g0); a[3] = cadd(f1, g1); a[7] = csub(f1, g1);
+}
+
+// exp(-i*pi*m/16), m = 0..7: the thread-independent part of the twist
+__device__ __constant__ double kTwistRe[8] = {1.0, 0.9807852804032304, 0.9238795325112867, 0.8314696123025452,
+                                              0.7071067811865476, 0.5555702330196023, 0.38268343236508984,
+                                              0.19509032201612833};
+__device__ __constant__ double kTwistIm[8] = {-0.0, -0.19509032201612825, -0.3826834323650898, -0.5555702330196022,
+                                              -0.7071067811865475, -0.8314696123025452, -0.9238795325112867,
+                                              -0.9807852804032304};
+
+// Per-thread twiddle bases, loaded once per kernel from the table E[x] = exp(-i*pi*x/1024), x < 2048.
+struct Twiddles {
+    double2 e1, s1, s2, s4;  // E(t), E(4t), E(8t), E(16t)     -> T_q = E(t*(4q+1))
+    double2 v1, v2, v4;      // E(32*t1), E(64*t1), E(128*t1)  -> W64^(t1*q2), t1 = t & 7
+    __device__ __forceinline__ void load(const double2* __restrict__ E, int t) {
+        e1 = E[t]; s1 = E[4 * t]; s2 = E[8 * t]; s4 = E[16 * t];
+        int t1 = t & 7;
+        v1 = E[32 * t1]; v2 = E[64 * t1]; v4 = E[128 * t1];
+    }
+};
+
+// Forward transform.  In: a[m] = z_{t+64m} (untwisted).  Out: a[q3] = Z_{q + 8*q2 + 64*q3}, v = q2 + 8q = t.
+// X1, X2: two 512-element double2 scratch buffers private to the 64-thread group.
+__device__ __forceinline__ void fft512_forward(double2 (&a)[8], const Twiddles& w, double2* X1, double2* X2, int t,
+                                               int bar_id) {
+#pragma unroll
+    for (int m = 1; m < 8; m++) a[m] = cmul(a[m], make_double2(kTwistRe[m], kTwistIm[m]));
+    dft8<false>(a);
+    {
+        double2 T1 = cmul(w.e1, w.s1), T2 = cmul(w.e1, w.s2), T3 = cmul(T1, w.s2), T4 = cmul(w.e1, w.s4);
+        double2 T5 = cmul(T1, w.s4), T6 = cmul(T2, w.s4), T7 = cmul(T3, w.s4);
+        a[0] = cmul(a[0], w.e1); a[1] = cmul(a[1], T1); a[2] = cmul(a[2], T2); a[3] = cmul(a[3], T3);
+        a[4] = cmul(a[4], T4); a[5] = cmul(a[5], T5); a[6] = cmul(a[6], T6); a[7] = cmul(a[7], T7);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) X1[q * 64 + t] = a[q];
+    group_sync(bar_id);
+    const int lo = t & 7, hi = t >> 3;
+#pragma unroll
+    for (int t2 = 0; t2 < 8; t2++) a[t2] = X1[hi * 64 + lo + 8 * t2];
+    dft8<false>(a);
+    {
+        double2 v3 = cmul(w.v1, w.v2), v5 = cmul(w.v1, w.v4), v6 = cmul(w.v2, w.v4), v7 = cmul(v3, w.v4);
+        a[1] = cmul(a[1], w.v1); a[2] = cmul(a[2], w.v2); a[3] = cmul(a[3], v3); a[4] = cmul(a[4], w.v4);
+        a[5] = cmul(a[5], v5); a[6] = cmul(a[6], v6); a[7] = cmul(a[7], v7);
+    }
+#pragma unroll
+    for (int q2 = 0; q2 < 8; q2++) X2[hi * 64 + q2 * 8 + (lo ^ q2)] = a[q2];
+    group_sync(bar_id);
+#pragma unroll
+    for (int t1 = 0; t1 < 8; t1++) a[t1] = X2[hi * 64 + lo * 8 + (t1 ^ lo)];
+    dft8<false>(a);
+}
+
+// Inverse transform, the mirror of fft512_forward.  In: a[q3] spectrum at thread v.  Out: a[m] = z_{t+64m}
+// scaled by 1/512 and untwisted, i.e. the folded coefficients (p_j - i*p_{j+512}).
+__device__ __forceinline__ void fft512_inverse(double2 (&a)[8], const Twiddles& w, double2* X1, double2* X2, int t,
+                                               int bar_id) {
+    const int lo = t & 7, hi = t >> 3;
+    dft8<true>(a);   // q3 -> t1
+    {
+        double2 v3 = cmul(w.v1, w.v2), v5 = cmul(w.v1, w.v4), v6 = cmul(w.v2, w.v4), v7 = cmul(v3, w.v4);
+        a[1] = cmulc(a[1], w.v1); a[2] = cmulc(a[2], w.v2); a[3] = cmulc(a[3], v3); a[4] = cmulc(a[4], w.v4);
+        a[5] = cmulc(a[5], v5); a[6] = cmulc(a[6], v6); a[7] = cmulc(a[7], v7);
+    }
+#pragma unroll
+    for (int t1 = 0; t1 < 8; t1++) X2[hi * 64 + lo * 8 + (t1 ^ lo)] = a[t1];
+    group_sync(bar_id);
+#pragma unroll
+    for (int q2 = 0; q2 < 8; q2++) a[q2] = X2[hi * 64 + q2 * 8 + (lo ^ q2)];
+    dft8<true>(a);   // q2 -> t2
+#pragma unroll
+    for (int t2 = 0; t2 < 8; t2++) X1[hi * 64 + lo + 8 * t2] = a[t2];
+    group_sync(bar_id);
+#pragma unroll
+    for (int q = 0; q < 8; q++) a[q] = X1[q * 64 + t];
+    {
+        double2 T1 = cmul(w.e1, w.s1), T2 = cmul(w.e1, w.s2), T3 = cmul(T1, w.s2), T4 = cmul(w.e1, w.s4);
+        double2 T5 = cmul(T1, w.s4), T6 = cmul(T2, w.s4), T7 = cmul(T3, w.s4);
+        a[0] = cmulc(a[0], w.e1); a[1] = cmulc(a[1], T1); a[2] = cmulc(a[2], T2); a[3] = cmulc(a[3], T3);
+        a[4] = cmulc(a[4], T4); a[5] = cmulc(a[5], T5); a[6] = cmulc(a[6], T6); a[7] = cmulc(a[7], T7);
+    }
+    dft8<true>(a);   // q -> m
+    constexpr double sc = 1.0 / 512.0;
+    a[0] = make_double2(a[0].x * sc, a[0].y * sc);
+#pragma unroll
+    for (int m = 1; m < 8; m++) a[m] = cmulc(a[m], make_double2(kTwistRe[m] * sc, kTwistIm[m] * sc));
+}
+
+// round-to-nearest-even to a 64-bit integer, keep the low 32 bits (polynomials.jl:115-116)
+__device__ __forceinline__ uint32_t round_to_u32(double x) { return (uint32_t)(unsigned long long)__double2ll_rn(x); }
+
+}  // namespace tfhe_b200
