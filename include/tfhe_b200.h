@@ -98,6 +98,8 @@ const char* tfhe_b200_last_error(const tfhe_b200_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches claim) */
 uint64_t tfhe_b200_kernel_launches(const tfhe_b200_ctx* ctx);
 int tfhe_b200_synchronize(tfhe_b200_ctx* ctx);
+/* measured FP64 FMA throughput of the context's device (roofline denominator of the transform kernels) */
+int tfhe_b200_measure_fp64_tflops(tfhe_b200_ctx* ctx, double* out_tflops);
 
 /* ---- key loading (K6) -------------------------------------------------------------------- */
 /* BootstrapKey (bootstrap.jl:1-16): takes the int32 coefficient form and performs

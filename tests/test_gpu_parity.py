@@ -171,7 +171,6 @@ def test_ragged_and_empty_batches(keys80, octx80, gctx80):
     for count in (0, 1, 3):      # odd counts exercise the partially filled last CTA
         bits = np.random.default_rng(count).integers(0, 2, (count, 2)).astype(bool)
         x, y = O.encrypt(rng, keys80, bits[:, 0]), O.encrypt(rng, keys80, bits[:, 1])
-        x, y = x.reshape(count, -1), y.reshape(count, -1)
         got = gctx80.gate(O.AND, x, y, count=count)
         assert got.shape == (count, keys80.params.n + 1)
         if count:

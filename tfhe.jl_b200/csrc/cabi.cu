@@ -510,3 +510,31 @@ int tfhe_b200_polymul_batch(tfhe_b200_ctx* ctx, const int32_t* x, const int32_t*
 }
 
 #include "mk_cabi.inc"
+
+// ---- measurement helper -------------------------------------------------------------------------------
+int tfhe_b200_measure_fp64_tflops(tfhe_b200_ctx* ctx, double* out_tflops) {
+    if (!ctx || !out_tflops) return TFHE_B200_EINVAL;
+    CU(cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, ctx->device));
+    const int blocks = prop.multiProcessorCount * 4, threads = 512, iters = 8192;
+    int rc;
+    if ((rc = reserve(ctx, ctx->bout, (size_t)blocks * threads * sizeof(double)))) return rc;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        CU(cudaEventRecord(e0, ctx->stream));
+        fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((double*)ctx->bout.p, 1.0000001, 1e-9, iters);
+        CU(cudaEventRecord(e1, ctx->stream));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        double tf = (double)blocks * threads * iters * 8 * 2 / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *out_tflops = best;
+    return 0;
+}

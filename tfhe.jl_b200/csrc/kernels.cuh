@@ -387,3 +387,20 @@ __global__ void lincomb_kernel(const int32_t* __restrict__ x, const int32_t* __r
 }
 
 }  // namespace tfhe_b200
+
+namespace tfhe_b200 {
+// Measures the FP64 FMA issue rate of the device (the roofline denominator of the transform kernels:
+// MEASURED_PEAKS.json only records HBM and bf16 peaks).  8 independent FMA chains per thread.
+__global__ void fp64_peak_kernel(double* out, double a, double b, int iters) {
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; it++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = fma(x[i], a, b);
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += x[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace tfhe_b200
