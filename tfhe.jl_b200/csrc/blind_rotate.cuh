@@ -1,0 +1,201 @@
+// blind_rotate.cuh — K3: the persistent blind-rotation kernel (bootstrap.jl:19-82) for sm_100a.
+//
+// One CTA keeps G gates resident for all n iterations: one 64-thread group per gate, the TLWE accumulator
+// of every gate in shared memory.  The G groups walk the bootstrapping key in lockstep, so each 16 KB key
+// chunk is fetched from L2 ONCE per CTA by a TMA bulk copy (cp.async.bulk, SASS UBLKCP) into a ring of
+// shared-memory stages and then read by all G gates with conflict-free LDS.128:
+//
+//   producer warp (1 elected lane):  wait empty[s] -> arrive.expect_tx(full[s], 16 KB) -> cp.async.bulk
+//   consumer groups (2 warps each):  forward FFT of a digit polynomial (no key needed) ->
+//                                    wait full[s] -> multiply-accumulate against the chunk -> arrive empty[s]
+//
+// The copy of chunk k+1.. overlaps the transform of chunk k, so L2 latency never reaches the FP64 pipe
+// (v1 read the key with ld.global.nc inside the MAC: ncu showed 44 % of all stall samples on those DFMAs
+// waiting on the long scoreboard, profiles/r1/).  L2->SM key traffic drops by G x.
+//
+// bootstrap.jl:34 skips iterations whose rotation is 0.  Lockstep groups cannot skip independently, so a
+// zero rotation is simply executed: temp = X^0*acc - acc = 0, all digits are 0 (tgsw.jl:99-117 maps 0 to 0),
+// the products are exactly 0 and the accumulator is unchanged — bit-identical to skipping.
+#pragma once
+#include "kernels.cuh"
+
+namespace tfhe_b200 {
+
+// ---- mbarrier / bulk-copy primitives (PTX) ----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy (TMA, no tensor map needed for a contiguous 1-D block), completion on an mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kChunkElems = 2 * kSpectrum;        // double2 per key chunk
+constexpr int kChunkBytes = kChunkElems * 16;     // 16 KB
+
+// View of the key ring.  Every consumer thread tracks (stage, phase); thread 0 of the CTA is also the
+// producer: just before it waits for chunk k it refills the stage that chunk k-1 occupied with chunk
+// k+STAGES-1 (all groups released it an FFT ago, so the wait on `empty` practically never blocks), which
+// keeps STAGES-1 chunks in flight without spending a warp — a 9th warp would put 3 warps on one SM
+// sub-partition and cap every thread at 168 registers (16K registers per sub-partition).
+template <int L, int NP, int STAGES> struct BkFromRing {
+    static constexpr int kChunksPerIter = 2 * L * NP;
+    const double2* ring; uint64_t* full; uint64_t* empty;
+    const double2* bk;        // start of the key, [n_iter][kChunksPerIter] chunks
+    int total;                // chunks in the whole walk
+    int k;                    // sequence number of the next chunk to consume
+    int stage; uint32_t phase;
+    bool producer;
+
+    // sequence number -> offset of the chunk in memory: consumption order is (c, r, half), storage (r, c, half)
+    __device__ __forceinline__ size_t chunk_offset(int seq) const {
+        int i = seq / kChunksPerIter, q = seq % kChunksPerIter;
+        int h = q % NP, cr = q / NP, r = cr % L, c = cr / L;
+        return ((size_t)i * kChunksPerIter + (size_t)((r * 2 + c) * NP + h)) * kChunkElems;
+    }
+    __device__ __forceinline__ void issue(int seq) {
+        const int s = seq % STAGES;
+        mbar_arrive_expect_tx(full + s, kChunkBytes);
+        bulk_copy_g2s(const_cast<double2*>(ring) + (size_t)s * kChunkElems, bk + chunk_offset(seq), kChunkBytes, full + s);
+    }
+    __device__ __forceinline__ void prologue() {
+        if (producer)
+            for (int seq = 0; seq < STAGES - 1 && seq < total; seq++) issue(seq);
+    }
+    __device__ __forceinline__ const double2* acquire(int /*chunk: consumption order is fixed*/) {
+        if (producer) {
+            const int seq = k + STAGES - 1;
+            if (seq < total) {
+                if (k >= 1) mbar_wait(empty + (seq % STAGES), ((k - 1) / STAGES) & 1);
+                issue(seq);
+            }
+        }
+        mbar_wait(full + stage, phase);
+        return ring + (size_t)stage * kChunkElems;
+    }
+    __device__ __forceinline__ void release() {
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(empty + stage);
+        k++;
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+    static __device__ __forceinline__ double2 load(const double2* p) { return *p; }
+};
+
+struct BlindRotateArgs {
+    const double2* bk_fft;   // [n][L][2][2][NP][512]
+    const double2* E;        // twiddle table, 2048 entries
+    // MODE 0 (bootstrap_wo_keyswitch with fused gate prologue): lin = ka*x + kb*y + (0, cb)
+    const int32_t* x; const int32_t* y;
+    int32_t ka, kb, cb, mu;
+    // MODE 1 (raw blind_rotate on given accumulators)
+    const int32_t* acc_in; const int32_t* bara_in;
+    int32_t* out;            // MODE 0: [count][N+1] extracted LWE; MODE 1: [count][2][N]
+    int n, n_iter, n_pad;
+    unsigned long long count;
+};
+
+// per-group shared memory: X1 + X2 (+ S1 when NP == 2) + acc (+ bara, n_pad words)
+__host__ __device__ constexpr int group_smem_bytes(int NP) {
+    return 2 * kSpectrum * 16 + (NP == 2 ? NP * kSpectrum * 16 : 0) + 2 * kN * 4;
+}
+__host__ __device__ constexpr size_t br_smem_bytes(int NP, int G, int STAGES, int n_pad) {
+    return (size_t)STAGES * kChunkBytes + 128 + (size_t)G * (group_smem_bytes(NP) + n_pad * 4);
+}
+
+template <int L, int BGBIT, int NP, int G, int STAGES, int MODE>
+__global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs A) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2* ring = reinterpret_cast<double2*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * kChunkBytes);
+    uint64_t* empty = full + STAGES;
+    unsigned char* groups = smem_raw + (size_t)STAGES * kChunkBytes + 128;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 2 * G); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    BkFromRing<L, NP, STAGES> bk{ring, full, empty, A.bk_fft, A.n_iter * 2 * L * NP, 0, 0, 0u, threadIdx.x == 0};
+    bk.prologue();   // the first STAGES-1 chunks are in flight while the gate prologue below runs
+
+    // ---------------- consumers: one 64-thread group per gate ----------------
+    const int t = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int bar_id = grp + 1;
+    unsigned char* base = groups + (size_t)grp * (group_smem_bytes(NP) + A.n_pad * 4);
+    double2* X1 = reinterpret_cast<double2*>(base);
+    double2* X2 = X1 + kSpectrum;
+    double2* S1 = X2 + kSpectrum;
+    int32_t* acc = reinterpret_cast<int32_t*>(S1 + (NP == 2 ? NP * kSpectrum : 0));
+    int32_t* bara = acc + 2 * kN;
+    const unsigned long long g = (unsigned long long)blockIdx.x * G + grp;
+    const bool valid = g < A.count;   // a group without a gate still walks the ring (on zeros) to keep the lockstep
+    Twiddles w; w.load(A.E, t);
+
+    if (!valid) {
+        for (int x = t; x < 2 * kN; x += 64) acc[x] = 0;
+        for (int i = t; i < A.n_iter; i += 64) bara[i] = 0;
+    } else if (MODE == 0) {
+        // gate prologue (gates.jl) + modulus switch (bootstrap.jl:74-75)
+        const int32_t* xr = A.x + g * (A.n + 1);
+        const int32_t* yr = A.y ? A.y + g * (A.n + 1) : nullptr;
+        for (int i = t; i < A.n; i += 64) {
+            uint32_t v = (uint32_t)A.ka * (uint32_t)xr[i];
+            if (yr) v += (uint32_t)A.kb * (uint32_t)yr[i];
+            bara[i] = modswitch2048((int32_t)v);
+        }
+        uint32_t vb = (uint32_t)A.ka * (uint32_t)xr[A.n] + (uint32_t)A.cb;
+        if (yr) vb += (uint32_t)A.kb * (uint32_t)yr[A.n];
+        const int barb = modswitch2048((int32_t)vb);
+        // acc = (0, X^{-barb} * (mu, ..., mu))   (bootstrap.jl:54-56,78)
+        const int s = (-barb) & 2047;
+        for (int x = t; x < kN; x += 64) {
+            acc[x] = 0;
+            int yy = (x - s) & 2047;
+            acc[kN + x] = (yy & 1024) ? (int32_t)(0u - (uint32_t)A.mu) : A.mu;
+        }
+    } else {
+        const int32_t* ain = A.acc_in + g * (2 * kN);
+        for (int x = t; x < 2 * kN; x += 64) acc[x] = ain[x];
+        for (int i = t; i < A.n_iter; i += 64) bara[i] = A.bara_in[g * A.n + i];
+    }
+    group_sync(bar_id);
+
+#pragma unroll 1
+    for (int i = 0; i < A.n_iter; i++)
+        extern_product_step<L, BGBIT, NP, true, true>(acc, bara[i], bk, w, X1, X2, S1, t, bar_id);   // bootstrap.jl:19-23
+
+    if (!valid) return;
+    if (MODE == 0) {
+        // tlwe_extract_sample (tlwe.jl:55-59): a = (p_0, -p_{N-1}, ..., -p_1), b = acc_b[0]
+        int32_t* o = A.out + g * (kN + 1);
+        for (int x = t; x < kN; x += 64) o[x] = x == 0 ? acc[0] : (int32_t)(0u - (uint32_t)acc[kN - x]);
+        if (t == 0) o[kN] = acc[kN];
+    } else {
+        int32_t* o = A.out + g * (2 * kN);
+        for (int x = t; x < 2 * kN; x += 64) o[x] = acc[x];
+    }
+}
+
+}  // namespace tfhe_b200

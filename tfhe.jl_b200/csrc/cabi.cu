@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "blind_rotate.cuh"
 #include "mk_kernels.cuh"
 
 using namespace tfhe_b200;
@@ -35,7 +36,7 @@ struct tfhe_b200_ctx {
     int device = 0;
     uint32_t flags = 0;
     int NP = 2;
-    int occ = 3;                     // CTAs (of 2 gates) per SM the blind-rotation kernel is compiled for
+    int G = 0;                       // gates per CTA of the blind-rotation kernel (0 = default, see launch_br_np)
     cudaStream_t stream = nullptr;   // used by the host-buffer entry points
     double2* d_E = nullptr;          // exp(-i*pi*x/1024), x < 2048
     double2* d_bk_fft = nullptr;     // single-key: [n][l][2][2][NP][512]; MK: [p][n][l*(2p+2)][NP][512]
@@ -83,10 +84,11 @@ int env_int(const char* name, int dflt) {
 }
 
 // ---- kernel dispatch ------------------------------------------------------------------------------
-template <int L, int BGBIT, int NP, int G, int MB, int MODE>
+template <int L, int BGBIT, int NP, int G, int STAGES, int MODE>
 int launch_br_g(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
-    auto kern = blind_rotate_kernel<L, BGBIT, NP, G, MB, MODE>;
-    size_t smem = (size_t)G * (kGroupSmemBytes + A.n_pad * 4);
+    auto kern = blind_rotate_kernel<L, BGBIT, NP, G, STAGES, MODE>;
+    const size_t smem = br_smem_bytes(NP, G, STAGES, A.n_pad);
+    if (smem > 227 * 1024) return fail(ctx, TFHE_B200_EINVAL, "LWE dimension too large for the shared-memory layout");
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned grid = (unsigned)((A.count + G - 1) / G);
     kern<<<grid, 64 * G, smem, s>>>(A);
@@ -94,14 +96,24 @@ int launch_br_g(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
     ctx->launches++;
     return 0;
 }
-// G = gates per CTA, MB = CTAs per SM the register allocation is tuned for (TFHE_B200_OCC)
+// G = gates resident per CTA (one CTA per SM), STAGES = depth of the TMA key ring.  TFHE_B200_G selects among
+// the compiled variants (development knob); the defaults are the fastest measured on B200 (profiles/).
 template <int L, int BGBIT, int NP, int MODE>
 int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
-    if (MODE == 1) return launch_br_g<L, BGBIT, NP, 2, 2, MODE>(ctx, A, s);
-    switch (ctx->occ) {
-        case 2: return launch_br_g<L, BGBIT, NP, 2, 2, MODE>(ctx, A, s);
-        case 4: return launch_br_g<L, BGBIT, NP, 2, 4, MODE>(ctx, A, s);
-        default: return launch_br_g<L, BGBIT, NP, 2, 3, MODE>(ctx, A, s);
+    if constexpr (MODE == 1) {
+        return launch_br_g<L, BGBIT, NP, 2, 2, MODE>(ctx, A, s);
+    } else if constexpr (NP == 1) {
+        switch (ctx->G) {
+            case 3: return launch_br_g<L, BGBIT, NP, 3, 4, MODE>(ctx, A, s);
+            case 5: return launch_br_g<L, BGBIT, NP, 5, 3, MODE>(ctx, A, s);
+            case 6: return launch_br_g<L, BGBIT, NP, 6, 3, MODE>(ctx, A, s);
+            default: return launch_br_g<L, BGBIT, NP, 4, 4, MODE>(ctx, A, s);   // 8 warps, 2 per sub-partition, no spills
+        }
+    } else {
+        switch (ctx->G) {
+            case 3: return launch_br_g<L, BGBIT, NP, 3, 4, MODE>(ctx, A, s);
+            default: return launch_br_g<L, BGBIT, NP, 4, 3, MODE>(ctx, A, s);
+        }
     }
 }
 template <int MODE>
@@ -256,7 +268,7 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
     tfhe_b200_ctx* c = new tfhe_b200_ctx();
     c->P = P; c->device = device_id; c->flags = flags;
     c->NP = (flags & TFHE_B200_FLAG_UNSPLIT_FFT) ? 1 : 2;
-    c->occ = env_int("TFHE_B200_OCC", 3);
+    c->G = env_int("TFHE_B200_G", 0);
     c->chunk = (size_t)env_int("TFHE_B200_CHUNK", 1 << 16);
     ctx = c;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);

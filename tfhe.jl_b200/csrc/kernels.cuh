@@ -87,14 +87,34 @@ __global__ void __launch_bounds__(64) bk_transform_kernel(const int32_t* __restr
 //   res_c' = sum_{r,c} digit_r(temp_c) (*) BK[r][c][c']                    (tgsw.jl:126-128)
 //   acc_c' = ACCUM ? acc_c' + res_c' : res_c'                              (bootstrap.jl:22)
 // bk_row points at [r][c][c'][piece][q3][v] for this key element.  The 64 threads of the group all call it.
-template <int L, int BGBIT, int NP, bool ROTSUB, bool ACCUM>
-__device__ __forceinline__ void extern_product_step(int32_t* acc, int abar, const double2* __restrict__ bk_row,
-                                                    const Twiddles& w, double2* X1, double2* X2, int t, int bar_id) {
+//
+// Output spectra: (k+1)*NP = 2*NP accumulators of 8 complex points per thread.  With NP == 1 both live in
+// registers.  With NP == 2 that would be 128 registers of accumulators alone (ncu, profiles/r1: 168-reg
+// build spilled 3.0e9 local ld/st per 4096 gates and wrote 15.9 GB to DRAM), so the two pieces of output
+// component 0 stay in registers and those of component 1 live in S1, a thread-private slice of shared
+// memory (slot e*64 + t is only ever touched by thread t: no barrier, conflict-free LDS.128/STS.128).
+template <int NP> struct SpectrumAcc { static constexpr int kRegComponents = NP == 1 ? 2 : 1; };
+
+// Where the bootstrapping-key spectra of one key element come from.  A "chunk" is 2 spectra = 16 KB:
+// chunk (r, c, half) = index (r*2 + c)*NP + half of the row; for NP == 1 it holds output components
+// c' = 0,1, for NP == 2 it holds the two 16-bit pieces of output component c' = half.
+struct BkFromGlobal {   // coalesced 16-byte read-only loads straight from L2 (stand-alone K2 kernel, tests)
+    const double2* row;
+    __device__ __forceinline__ const double2* acquire(int chunk) { return row + (size_t)chunk * 2 * kSpectrum; }
+    __device__ __forceinline__ void release() {}
+    static __device__ __forceinline__ double2 load(const double2* p) { return __ldg(p); }
+};
+
+template <int L, int BGBIT, int NP, bool ROTSUB, bool ACCUM, class BK>
+__device__ __forceinline__ void extern_product_step(int32_t* acc, int abar, BK& bk,
+                                                    const Twiddles& w, double2* X1, double2* X2, double2* S1, int t,
+                                                    int bar_id) {
     constexpr uint32_t offset = decomp_offset<L, BGBIT>();
+    constexpr int CR = SpectrumAcc<NP>::kRegComponents;
     const int s = abar & 2047;
-    double2 o[2][NP][8];
+    double2 o[CR][NP][8];
 #pragma unroll
-    for (int c2 = 0; c2 < 2; c2++)
+    for (int c2 = 0; c2 < CR; c2++)
 #pragma unroll
         for (int pc = 0; pc < NP; pc++)
 #pragma unroll
@@ -122,29 +142,46 @@ __device__ __forceinline__ void extern_product_step(int32_t* acc, int abar, cons
             for (int m = 0; m < 8; m++)
                 a[m] = make_double2((double)digit<BGBIT>(tl[m], r), -(double)digit<BGBIT>(th[m], r));
             fft512_forward(a, w, X1, X2, t, bar_id);
-            const double2* b = bk_row + (size_t)((r * 2 + c) * 2 * NP) * kSpectrum + t;
+            {
+                // first chunk of (r, c): both output components (NP == 1) or the two pieces of component 0
+                const double2* b = bk.acquire((r * 2 + c) * NP) + t;
 #pragma unroll
-            for (int c2 = 0; c2 < 2; c2++)
+                for (int sp = 0; sp < 2; sp++)
 #pragma unroll
-                for (int pc = 0; pc < NP; pc++)
+                    for (int q = 0; q < 8; q++)
+                        cmac(NP == 1 ? o[sp % CR][0][q] : o[0][sp % NP][q], a[q], BK::load(b + (sp * 8 + q) * 64));
+                bk.release();
+            }
+            if (NP == 2) {
+                // second chunk: the two pieces of output component 1, accumulated in S1
+                const double2* b = bk.acquire((r * 2 + c) * NP + 1) + t;
+                const bool first = (c == 0 && r == 0);
 #pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        double2 bv = __ldg(b + ((c2 * NP + pc) * 8 + q) * 64);
-                        cmac(o[c2][pc][q], a[q], bv);
-                    }
+                for (int e = 0; e < 16; e++) {
+                    double2 sv = first ? make_double2(0.0, 0.0) : S1[e * 64 + t];
+                    cmac(sv, a[e & 7], BK::load(b + e * 64));
+                    S1[e * 64 + t] = sv;
+                }
+                bk.release();
+            }
         }
     }
     // every thread has finished reading acc and X2 (last forward) before anyone overwrites them
     group_sync(bar_id);
 #pragma unroll
     for (int c2 = 0; c2 < 2; c2++) {
+        double2 (&oc)[NP][8] = o[CR == 1 ? 0 : c2];
+        if (CR == 1 && c2 == 1) {
+#pragma unroll
+            for (int e = 0; e < NP * 8; e++) oc[e >> 3][e & 7] = S1[e * 64 + t];
+        }
         uint32_t rl[8], rh[8];
 #pragma unroll
         for (int pc = 0; pc < NP; pc++) {
-            fft512_inverse(o[c2][pc], w, X1, X2, t, bar_id);
+            fft512_inverse(oc[pc], w, X1, X2, t, bar_id);
 #pragma unroll
             for (int m = 0; m < 8; m++) {
-                uint32_t vl = round_to_u32(o[c2][pc][m].x), vh = round_to_u32(-o[c2][pc][m].y);
+                uint32_t vl = round_to_u32(oc[pc][m].x), vh = round_to_u32(-oc[pc][m].y);
                 if (pc == 0) { rl[m] = vl; rh[m] = vh; }
                 else { rl[m] += vl << 16; rh[m] += vh << 16; }
             }
@@ -160,83 +197,6 @@ __device__ __forceinline__ void extern_product_step(int32_t* acc, int abar, cons
     group_sync(bar_id);
 }
 
-// ------------------------------------------------------------------------------------------------
-// K3: blind rotation.  One 64-thread group per gate, G groups per CTA; the TLWE accumulator stays in
-// shared memory for all n iterations; BK rows are streamed from L2 with coalesced 16-byte loads.
-struct BlindRotateArgs {
-    const double2* bk_fft;   // [n][L][2][2][NP][512]
-    const double2* E;        // twiddle table, 2048 entries
-    // MODE 0 (bootstrap_wo_keyswitch with fused gate prologue): lin = ka*x + kb*y + (0, cb)
-    const int32_t* x; const int32_t* y;
-    int32_t ka, kb, cb, mu;
-    // MODE 1 (raw blind_rotate on given accumulators)
-    const int32_t* acc_in; const int32_t* bara_in;
-    int32_t* out;            // MODE 0: [count][N+1] extracted LWE; MODE 1: [count][2][N]
-    int n, n_iter, n_pad;
-    unsigned long long count;
-};
-
-constexpr int kGroupSmemBytes = 2 * kN * 4 + 2 * kSpectrum * 16;   // acc + X1 + X2
-
-template <int L, int BGBIT, int NP, int G, int MB, int MODE>
-__global__ void __launch_bounds__(64 * G, MB) blind_rotate_kernel(BlindRotateArgs A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int t = threadIdx.x & 63, grp = threadIdx.x >> 6;
-    const int bar_id = grp + 1;
-    unsigned char* base = smem_raw + (size_t)grp * (kGroupSmemBytes + A.n_pad * 4);
-    double2* X1 = reinterpret_cast<double2*>(base);
-    double2* X2 = X1 + kSpectrum;
-    int32_t* acc = reinterpret_cast<int32_t*>(X2 + kSpectrum);
-    int32_t* bara = acc + 2 * kN;
-    const unsigned long long g = (unsigned long long)blockIdx.x * G + grp;
-    if (g >= A.count) return;   // whole group exits together; named barriers are per group
-    Twiddles w; w.load(A.E, t);
-
-    if (MODE == 0) {
-        // gate prologue (gates.jl) + modulus switch (bootstrap.jl:74-75)
-        const int32_t* xr = A.x + g * (A.n + 1);
-        const int32_t* yr = A.y ? A.y + g * (A.n + 1) : nullptr;
-        for (int i = t; i < A.n; i += 64) {
-            uint32_t v = (uint32_t)A.ka * (uint32_t)xr[i];
-            if (yr) v += (uint32_t)A.kb * (uint32_t)yr[i];
-            bara[i] = modswitch2048((int32_t)v);
-        }
-        uint32_t vb = (uint32_t)A.ka * (uint32_t)xr[A.n] + (uint32_t)A.cb;
-        if (yr) vb += (uint32_t)A.kb * (uint32_t)yr[A.n];
-        const int barb = modswitch2048((int32_t)vb);
-        // acc = (0, X^{-barb} * (mu, ..., mu))   (bootstrap.jl:54-56,78)
-        const int s = (-barb) & 2047;
-        for (int x = t; x < kN; x += 64) {
-            acc[x] = 0;
-            int yy = (x - s) & 2047;
-            acc[kN + x] = (yy & 1024) ? (int32_t)(0u - (uint32_t)A.mu) : A.mu;
-        }
-    } else {
-        const int32_t* ain = A.acc_in + g * (2 * kN);
-        for (int x = t; x < 2 * kN; x += 64) acc[x] = ain[x];
-        for (int i = t; i < A.n_iter; i += 64) bara[i] = A.bara_in[g * A.n + i];
-    }
-    group_sync(bar_id);
-
-    const size_t row = (size_t)L * 2 * 2 * NP * kSpectrum;
-#pragma unroll 1
-    for (int i = 0; i < A.n_iter; i++) {
-        const int abar = bara[i];
-        if (abar == 0) continue;   // bootstrap.jl:34 (uniform across the group)
-        extern_product_step<L, BGBIT, NP, true, true>(acc, abar, A.bk_fft + (size_t)i * row, w, X1, X2, t, bar_id);
-    }
-
-    if (MODE == 0) {
-        // tlwe_extract_sample (tlwe.jl:55-59): a = (p_0, -p_{N-1}, ..., -p_1), b = acc_b[0]
-        int32_t* o = A.out + g * (kN + 1);
-        for (int x = t; x < kN; x += 64) o[x] = x == 0 ? acc[0] : (int32_t)(0u - (uint32_t)acc[kN - x]);
-        if (t == 0) o[kN] = acc[kN];
-    } else {
-        int32_t* o = A.out + g * (2 * kN);
-        for (int x = t; x < 2 * kN; x += 64) o[x] = acc[x];
-    }
-}
-
 // K2 as a stand-alone batch kernel (parity tests of tgsw_extern_mul): one group per product
 template <int L, int BGBIT, int NP>
 __global__ void __launch_bounds__(64) extern_product_kernel(const double2* __restrict__ bk_fft,
@@ -246,6 +206,7 @@ __global__ void __launch_bounds__(64) extern_product_kernel(const double2* __res
                                                             int32_t* __restrict__ out) {
     __shared__ double2 X1[512];
     __shared__ double2 X2[512];
+    __shared__ double2 S1[NP == 2 ? NP * kSpectrum : 1];
     __shared__ int32_t acc[2 * kN];
     const int t = threadIdx.x;
     Twiddles w; w.load(E, t);
@@ -253,7 +214,8 @@ __global__ void __launch_bounds__(64) extern_product_kernel(const double2* __res
     for (int x = t; x < 2 * kN; x += 64) acc[x] = acc_in[g * 2 * kN + x];
     __syncthreads();
     const size_t row = (size_t)L * 2 * 2 * NP * kSpectrum;
-    extern_product_step<L, BGBIT, NP, false, false>(acc, 0, bk_fft + (size_t)bk_index[g] * row, w, X1, X2, t, 0);
+    BkFromGlobal bk{bk_fft + (size_t)bk_index[g] * row};
+    extern_product_step<L, BGBIT, NP, false, false>(acc, 0, bk, w, X1, X2, S1, t, 0);
     for (int x = t; x < 2 * kN; x += 64) out[g * 2 * kN + x] = acc[x];
 }
 
