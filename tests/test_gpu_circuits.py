@@ -1,0 +1,48 @@
+"""BASELINE.json configs #1 and #4 as GPU parity cases: dependent gate circuits driven level by level through
+the mirrored API (each level is one batched C-ABI call)."""
+import numpy as np
+import pytest
+
+import tfhe_jl_b200 as T
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def keypair():
+    rng = np.random.default_rng(123)
+    return rng, *T.make_key_pair(rng)
+
+
+def bits_of(v, n):
+    return np.array([(v >> i) & 1 for i in range(n)], dtype=bool)
+
+
+def test_tutorial_minimum_circuit(keypair):
+    """examples/tutorial.jl: encrypted 16-bit minimum of 2017 and 42 -> 42 (80 blind rotations, depth 33)."""
+    rng, sk, ck = keypair
+    a, b = T.encrypt(rng, sk, bits_of(2017, 16)), T.encrypt(rng, sk, bits_of(42, 16))
+    carry = T.gate_constant(ck, False)                                  # tutorial.jl:53
+    for i in range(16):                                                 # tutorial.jl:55-57, 42-45
+        carry = T.gate_mux(ck, T.gate_xnor(ck, a[i], b[i]), carry, a[i])
+    sel = T.LweSample(np.repeat(carry.data[None, :], 16, axis=0))
+    res = T.gate_mux(ck, sel, b, a)                                     # tutorial.jl:61 (16 independent MUXes, one call)
+    assert sum(int(v) << i for i, v in enumerate(T.decrypt(sk, res))) == 42
+
+
+def test_ripple_carry_adder_32bit(keypair):
+    """32-bit ripple-carry adder over encrypted bits (not in the reference; built from its gates):
+    sum_i = a_i ^ b_i ^ c_i, c_{i+1} = MUX(a_i ^ b_i, c_i, a_i).  Several additions run side by side as a batch."""
+    rng, sk, ck = keypair
+    xs = np.array([0xDEADBEEF, 123456789, 0xFFFFFFFF, 0], dtype=np.uint64)
+    ys = np.array([0x12345678, 987654321, 1, 0], dtype=np.uint64)
+    A = [T.encrypt(rng, sk, np.array([(int(x) >> i) & 1 for x in xs], dtype=bool)) for i in range(32)]
+    B = [T.encrypt(rng, sk, np.array([(int(y) >> i) & 1 for y in ys], dtype=bool)) for i in range(32)]
+    carry = T.gate_constant(ck, np.zeros(len(xs), dtype=bool))
+    out = np.zeros(len(xs), dtype=np.uint64)
+    for i in range(32):
+        axb = T.gate_xor(ck, A[i], B[i])
+        s = T.gate_xor(ck, axb, carry)
+        carry = T.gate_mux(ck, axb, carry, A[i])
+        out |= T.decrypt(sk, s).astype(np.uint64) << np.uint64(i)
+    assert np.array_equal(out, (xs + ys) & np.uint64(0xFFFFFFFF))

@@ -5,7 +5,8 @@
 // chunk is fetched from L2 ONCE per CTA by a TMA bulk copy (cp.async.bulk, SASS UBLKCP) into a ring of
 // shared-memory stages and then read by all G gates with conflict-free LDS.128:
 //
-//   producer warp (1 elected lane):  wait empty[s] -> arrive.expect_tx(full[s], 16 KB) -> cp.async.bulk
+//   producer (thread 0 of the CTA):  wait empty[s] -> arrive.expect_tx(full[s], 16 KB) -> cp.async.bulk,
+//                                    STAGES-1 chunks ahead of its own consumption
 //   consumer groups (2 warps each):  forward FFT of a digit polynomial (no key needed) ->
 //                                    wait full[s] -> multiply-accumulate against the chunk -> arrive empty[s]
 //
