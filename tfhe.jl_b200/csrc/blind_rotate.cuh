@@ -19,6 +19,7 @@
 // the products are exactly 0 and the accumulator is unchanged — bit-identical to skipping.
 #pragma once
 #include "kernels.cuh"
+#include "tmem.cuh"
 
 namespace tfhe_b200 {
 
@@ -104,6 +105,85 @@ template <int L, int NP, int STAGES> struct BkFromRing {
     static __device__ __forceinline__ double2 load(const double2* p) { return *p; }
 };
 
+// K2 with the (k+1)*NP output spectra held in TENSOR MEMORY instead of registers (tmem.cuh).  The register
+// version (kernels.cuh) needs 64 / 128 registers of accumulators per thread, which limits K3 to 8 warps per
+// SM; with the accumulators in TMEM a thread needs < 168 registers, 12 warps (6 gates) fit, and the
+// read-modify-write of the accumulators runs on the TMEM datapath (LDTM/STTM), off the shared-memory pipe.
+// `tm` is the TMEM address of this thread's row (lane and first column already applied); the accumulator of
+// output component c2, piece pc occupies columns [(c2*NP + pc)*32, +32).
+template <int L, int BGBIT, int NP, class BK>
+__device__ __forceinline__ void extern_product_step_tmem(int32_t* acc, int abar, BK& bk, const Twiddles& w, double2* X1,
+                                                         double2* X2, uint32_t tm, int t, int bar_id) {
+    constexpr uint32_t offset = decomp_offset<L, BGBIT>();
+    const int s = abar & 2047;
+#pragma unroll 1
+    for (int c = 0; c < 2; c++) {
+        const int32_t* p = acc + c * kN;
+        uint32_t tl[8], th[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            int j = t + 64 * m;
+            tl[m] = (uint32_t)rot_coeff(p, j, s) - (uint32_t)p[j] + offset;                 // bootstrap.jl:21
+            th[m] = (uint32_t)rot_coeff(p, j + 512, s) - (uint32_t)p[j + 512] + offset;
+        }
+#pragma unroll 1
+        for (int r = 0; r < L; r++) {
+            double2 a[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++)
+                a[m] = make_double2((double)digit<BGBIT>(tl[m], r), -(double)digit<BGBIT>(th[m], r));   // tgsw.jl:104-116
+            fft512_forward(a, w, X1, X2, t, bar_id);
+            const bool first = (c == 0 && r == 0);
+            if (!first) tmem_wait_st();   // this thread's previous accumulator stores have landed
+#pragma unroll
+            for (int half = 0; half < NP; half++) {
+                const double2* b = bk.acquire((r * 2 + c) * NP + half) + t;
+#pragma unroll
+                for (int sp = 0; sp < 2; sp++) {
+                    const uint32_t col = tm + (uint32_t)((NP == 1 ? sp : half * 2 + sp) * 32);
+                    double2 o[8];
+                    if (first) {
+#pragma unroll
+                        for (int q = 0; q < 8; q++) o[q] = make_double2(0.0, 0.0);
+                    } else {
+                        tmem_load_spectrum(col, o);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; q++) cmac(o[q], a[q], BK::load(b + (sp * 8 + q) * 64));      // tgsw.jl:128
+                    tmem_store_spectrum(col, o);
+                }
+                bk.release();
+            }
+        }
+    }
+    tmem_wait_st();
+    group_sync(bar_id);   // all reads of acc and of X2 (last forward) are done
+#pragma unroll 1
+    for (int c2 = 0; c2 < 2; c2++) {
+        uint32_t rl[8], rh[8];
+#pragma unroll
+        for (int pc = 0; pc < NP; pc++) {
+            double2 o[8];
+            tmem_load_spectrum(tm + (uint32_t)((c2 * NP + pc) * 32), o);
+            fft512_inverse(o, w, X1, X2, t, bar_id);
+#pragma unroll
+            for (int m = 0; m < 8; m++) {
+                uint32_t vl = round_to_u32(o[m].x), vh = round_to_u32(-o[m].y);                       // polynomials.jl:115-116
+                if (pc == 0) { rl[m] = vl; rh[m] = vh; }
+                else { rl[m] += vl << 16; rh[m] += vh << 16; }
+            }
+        }
+        int32_t* p = acc + c2 * kN;
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            int j = t + 64 * m;
+            p[j] = (int32_t)((uint32_t)p[j] + rl[m]);                                               // bootstrap.jl:22
+            p[j + 512] = (int32_t)((uint32_t)p[j + 512] + rh[m]);
+        }
+    }
+    group_sync(bar_id);
+}
+
 struct BlindRotateArgs {
     const double2* bk_fft;   // [n][L][2][2][NP][512]
     const double2* E;        // twiddle table, 2048 entries
@@ -117,17 +197,28 @@ struct BlindRotateArgs {
     unsigned long long count;
 };
 
-// per-group shared memory: X1 + X2 (+ S1 when NP == 2) + acc (+ bara, n_pad words)
-__host__ __device__ constexpr int group_smem_bytes(int NP) {
-    return 2 * kSpectrum * 16 + (NP == 2 ? NP * kSpectrum * 16 : 0) + 2 * kN * 4;
-}
+// per-group shared memory: X1 + X2 + acc (+ bara, n_pad words)
+__host__ __device__ constexpr int group_smem_bytes(int /*NP*/) { return 2 * kSpectrum * 16 + 2 * kN * 4; }
 __host__ __device__ constexpr size_t br_smem_bytes(int NP, int G, int STAGES, int n_pad) {
     return (size_t)STAGES * kChunkBytes + 128 + (size_t)G * (group_smem_bytes(NP) + n_pad * 4);
 }
 
-template <int L, int BGBIT, int NP, int G, int STAGES, int MODE>
+// TMEM columns to allocate when the accumulators live in tensor memory: warps that share a lane quarter
+// (warp % 4) get disjoint column ranges of 64*NP columns each; allocations are powers of two.
+__host__ __device__ constexpr int br_tmem_cols(int NP, int G) {
+    int need = ((2 * G + 3) / 4) * 64 * NP, c = 32;
+    while (c < need) c *= 2;
+    return c;
+}
+
+template <int L, int BGBIT, int NP, int G, int STAGES, int MODE, bool TM = false>
 __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint32_t s_tmem_base;
+    if (TM) {
+        if ((threadIdx.x >> 5) == 0) tmem_alloc<br_tmem_cols(NP, G)>(&s_tmem_base);
+        tmem_fence_before_sync();
+    }
     double2* ring = reinterpret_cast<double2*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * kChunkBytes);
     uint64_t* empty = full + STAGES;
@@ -138,6 +229,12 @@ __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs
         mbar_fence_init();
     }
     __syncthreads();
+    uint32_t tm = 0;
+    if (TM) {
+        tmem_fence_after_sync();
+        const int warp = threadIdx.x >> 5;
+        tm = s_tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 64 * NP);
+    }
     BkFromRing<L, NP, STAGES> bk{ring, full, empty, A.bk_fft, A.n_iter * 2 * L * NP, 0, 0, 0u, threadIdx.x == 0};
     bk.prologue();   // the first STAGES-1 chunks are in flight while the gate prologue below runs
 
@@ -147,8 +244,7 @@ __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs
     unsigned char* base = groups + (size_t)grp * (group_smem_bytes(NP) + A.n_pad * 4);
     double2* X1 = reinterpret_cast<double2*>(base);
     double2* X2 = X1 + kSpectrum;
-    double2* S1 = X2 + kSpectrum;
-    int32_t* acc = reinterpret_cast<int32_t*>(S1 + (NP == 2 ? NP * kSpectrum : 0));
+    int32_t* acc = reinterpret_cast<int32_t*>(X2 + kSpectrum);
     int32_t* bara = acc + 2 * kN;
     const unsigned long long g = (unsigned long long)blockIdx.x * G + grp;
     const bool valid = g < A.count;   // a group without a gate still walks the ring (on zeros) to keep the lockstep
@@ -184,11 +280,13 @@ __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs
     group_sync(bar_id);
 
 #pragma unroll 1
-    for (int i = 0; i < A.n_iter; i++)
-        extern_product_step<L, BGBIT, NP, true, true>(acc, bara[i], bk, w, X1, X2, S1, t, bar_id);   // bootstrap.jl:19-23
+    for (int i = 0; i < A.n_iter; i++) {   // bootstrap.jl:19-23
+        if (TM) extern_product_step_tmem<L, BGBIT, NP>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id);
+        else extern_product_step<L, BGBIT, NP, true, true>(acc, bara[i], bk, w, X1, X2, t, bar_id);
+    }
 
-    if (!valid) return;
-    if (MODE == 0) {
+    if (!valid) {
+    } else if (MODE == 0) {
         // tlwe_extract_sample (tlwe.jl:55-59): a = (p_0, -p_{N-1}, ..., -p_1), b = acc_b[0]
         int32_t* o = A.out + g * (kN + 1);
         for (int x = t; x < kN; x += 64) o[x] = x == 0 ? acc[0] : (int32_t)(0u - (uint32_t)acc[kN - x]);
@@ -196,6 +294,11 @@ __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs
     } else {
         int32_t* o = A.out + g * (2 * kN);
         for (int x = t; x < 2 * kN; x += 64) o[x] = acc[x];
+    }
+    if (TM) {
+        tmem_fence_before_sync();
+        __syncthreads();
+        if ((threadIdx.x >> 5) == 0) tmem_dealloc<br_tmem_cols(NP, G)>(s_tmem_base);
     }
 }
 

@@ -84,9 +84,9 @@ int env_int(const char* name, int dflt) {
 }
 
 // ---- kernel dispatch ------------------------------------------------------------------------------
-template <int L, int BGBIT, int NP, int G, int STAGES, int MODE>
+template <int L, int BGBIT, int NP, int G, int STAGES, int MODE, bool TM = false>
 int launch_br_g(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
-    auto kern = blind_rotate_kernel<L, BGBIT, NP, G, STAGES, MODE>;
+    auto kern = blind_rotate_kernel<L, BGBIT, NP, G, STAGES, MODE, TM>;
     const size_t smem = br_smem_bytes(NP, G, STAGES, A.n_pad);
     if (smem > 227 * 1024) return fail(ctx, TFHE_B200_EINVAL, "LWE dimension too large for the shared-memory layout");
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -102,17 +102,19 @@ template <int L, int BGBIT, int NP, int MODE>
 int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
     if constexpr (MODE == 1) {
         return launch_br_g<L, BGBIT, NP, 2, 2, MODE>(ctx, A, s);
-    } else if constexpr (NP == 1) {
-        switch (ctx->G) {
-            case 3: return launch_br_g<L, BGBIT, NP, 3, 4, MODE>(ctx, A, s);
-            case 5: return launch_br_g<L, BGBIT, NP, 5, 3, MODE>(ctx, A, s);
-            case 6: return launch_br_g<L, BGBIT, NP, 6, 3, MODE>(ctx, A, s);
-            default: return launch_br_g<L, BGBIT, NP, 4, 4, MODE>(ctx, A, s);   // 8 warps, 2 per sub-partition, no spills
-        }
     } else {
+        // 4 gates = 8 warps = 2 per SM sub-partition: the only shape that leaves 255 registers per thread
         switch (ctx->G) {
-            case 3: return launch_br_g<L, BGBIT, NP, 3, 4, MODE>(ctx, A, s);
-            default: return launch_br_g<L, BGBIT, NP, 4, 3, MODE>(ctx, A, s);
+            case 104: return launch_br_g<L, BGBIT, NP, 4, 6, MODE, true>(ctx, A, s);   // TMEM accumulators
+            case 105: return launch_br_g<L, BGBIT, NP, 5, 4, MODE, true>(ctx, A, s);
+            case 106: return launch_br_g<L, BGBIT, NP, 6, 3, MODE, true>(ctx, A, s);
+            case 107: return launch_br_g<L, BGBIT, NP, 7, 2, MODE, true>(ctx, A, s);
+            case 4: return launch_br_g<L, BGBIT, NP, 4, 6, MODE>(ctx, A, s);           // register accumulators
+            default:
+                // measured (profiles/r1): with one 32-bit piece the 64 accumulator registers fit and registers win
+                // (142 k vs 135 k gates/s); with two pieces (128 registers) TMEM wins (96 k vs 88 k gates/s)
+                if constexpr (NP == 1) return launch_br_g<L, BGBIT, NP, 4, 6, MODE>(ctx, A, s);
+                else return launch_br_g<L, BGBIT, NP, 4, 6, MODE, true>(ctx, A, s);
         }
     }
 }
@@ -141,6 +143,13 @@ int launch_extern(tfhe_b200_ctx* ctx, const int32_t* acc, const int32_t* idx, in
     return 0;
 }
 
+int launch_keyswitch_args(tfhe_b200_ctx* ctx, const KeyswitchArgs& A, size_t count, cudaStream_t s) {
+    keyswitch_kernel<<<(unsigned)count, A.stride / 4, (size_t)A.Nk * sizeof(int32_t), s>>>(A, count);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
 // keyswitch of ciphertexts [count][Nk+1] -> [count][n+1] with key set `party`
 int launch_keyswitch(tfhe_b200_ctx* ctx, const int32_t* in, int32_t* out, size_t count, cudaStream_t s) {
     if (count == 0) return 0;
@@ -150,10 +159,7 @@ int launch_keyswitch(tfhe_b200_ctx* ctx, const int32_t* in, int32_t* out, size_t
     A.n = P.n; A.Nk = P.N * P.k; A.t = P.t; A.basebit = P.basebit; A.stride = ctx->ksk_stride;
     A.in_stride = A.Nk + 1; A.in_offset = 0; A.in_b_offset = A.Nk;
     A.out_stride = P.n + 1; A.out_offset = 0; A.b_offset = P.n; A.b_mode = 0;
-    keyswitch_kernel<<<(unsigned)count, ctx->ksk_stride / 4, A.Nk * sizeof(int32_t), s>>>(A);
-    CU(cudaGetLastError());
-    ctx->launches++;
-    return 0;
+    return launch_keyswitch_args(ctx, A, count, s);
 }
 
 int launch_lincomb(tfhe_b200_ctx* ctx, const int32_t* x, const int32_t* y, int32_t* out, int32_t ka, int32_t kb,
@@ -259,7 +265,8 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
     const auto& P = *params;
     if (P.N != 1024 || P.k != 1) return fail(nullptr, TFHE_B200_EINVAL, "only N = 1024, k = 1 are supported");
     if (P.n < 1 || P.n > 4096) return fail(nullptr, TFHE_B200_EINVAL, "n out of range");
-    if (P.t < 1 || P.basebit < 1 || P.t * P.basebit > 31 || P.basebit > 4) return fail(nullptr, TFHE_B200_EINVAL, "bad keyswitch parameters");
+    if (P.t < 1 || P.basebit < 1 || P.t * P.basebit > 31 || P.basebit > 4 || P.n > 4000)
+        return fail(nullptr, TFHE_B200_EINVAL, "bad keyswitch parameters (the reference's sets use t = 8, basebit = 2)");
     if (P.parties == 1 ? !single_key_supported(P.l, P.bgbit) : !mk_supported(P.parties, P.l, P.bgbit))
         return fail(nullptr, TFHE_B200_EINVAL, "unsupported (parties, l, bgbit): supported are the reference's parameter sets");
     if (tfhe_b200_device_count() <= device_id || device_id < 0)

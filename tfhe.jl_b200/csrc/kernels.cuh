@@ -88,13 +88,11 @@ __global__ void __launch_bounds__(64) bk_transform_kernel(const int32_t* __restr
 //   acc_c' = ACCUM ? acc_c' + res_c' : res_c'                              (bootstrap.jl:22)
 // bk_row points at [r][c][c'][piece][q3][v] for this key element.  The 64 threads of the group all call it.
 //
-// Output spectra: (k+1)*NP = 2*NP accumulators of 8 complex points per thread.  With NP == 1 both live in
-// registers.  With NP == 2 that would be 128 registers of accumulators alone (ncu, profiles/r1: 168-reg
-// build spilled 3.0e9 local ld/st per 4096 gates and wrote 15.9 GB to DRAM), so the two pieces of output
-// component 0 stay in registers and those of component 1 live in S1, a thread-private slice of shared
-// memory (slot e*64 + t is only ever touched by thread t: no barrier, conflict-free LDS.128/STS.128).
-template <int NP> struct SpectrumAcc { static constexpr int kRegComponents = NP == 1 ? 2 : 1; };
-
+// Output spectra: (k+1)*NP accumulators of 8 complex points per thread, all in registers (64 registers for
+// NP == 1, 128 for NP == 2).  That only works because K3 runs 8 warps per SM (2 per sub-partition, up to 255
+// registers per thread): the 168-register v1 build spilled 3.0e9 local ld/st per 4096 gates and wrote 15.9 GB
+// to DRAM, and keeping half of them in shared memory (v2/v3a) cost 23 % more shared-memory wavefronts.
+//
 // Where the bootstrapping-key spectra of one key element come from.  A "chunk" is 2 spectra = 16 KB:
 // chunk (r, c, half) = index (r*2 + c)*NP + half of the row; for NP == 1 it holds output components
 // c' = 0,1, for NP == 2 it holds the two 16-bit pieces of output component c' = half.
@@ -107,14 +105,12 @@ struct BkFromGlobal {   // coalesced 16-byte read-only loads straight from L2 (s
 
 template <int L, int BGBIT, int NP, bool ROTSUB, bool ACCUM, class BK>
 __device__ __forceinline__ void extern_product_step(int32_t* acc, int abar, BK& bk,
-                                                    const Twiddles& w, double2* X1, double2* X2, double2* S1, int t,
-                                                    int bar_id) {
+                                                    const Twiddles& w, double2* X1, double2* X2, int t, int bar_id) {
     constexpr uint32_t offset = decomp_offset<L, BGBIT>();
-    constexpr int CR = SpectrumAcc<NP>::kRegComponents;
     const int s = abar & 2047;
-    double2 o[CR][NP][8];
+    double2 o[2][NP][8];
 #pragma unroll
-    for (int c2 = 0; c2 < CR; c2++)
+    for (int c2 = 0; c2 < 2; c2++)
 #pragma unroll
         for (int pc = 0; pc < NP; pc++)
 #pragma unroll
@@ -142,26 +138,15 @@ __device__ __forceinline__ void extern_product_step(int32_t* acc, int abar, BK& 
             for (int m = 0; m < 8; m++)
                 a[m] = make_double2((double)digit<BGBIT>(tl[m], r), -(double)digit<BGBIT>(th[m], r));
             fft512_forward(a, w, X1, X2, t, bar_id);
-            {
-                // first chunk of (r, c): both output components (NP == 1) or the two pieces of component 0
-                const double2* b = bk.acquire((r * 2 + c) * NP) + t;
+#pragma unroll
+            for (int half = 0; half < NP; half++) {
+                // chunk (r, c, half): both output components (NP == 1) or the two pieces of component `half`
+                const double2* b = bk.acquire((r * 2 + c) * NP + half) + t;
 #pragma unroll
                 for (int sp = 0; sp < 2; sp++)
 #pragma unroll
                     for (int q = 0; q < 8; q++)
-                        cmac(NP == 1 ? o[sp % CR][0][q] : o[0][sp % NP][q], a[q], BK::load(b + (sp * 8 + q) * 64));
-                bk.release();
-            }
-            if (NP == 2) {
-                // second chunk: the two pieces of output component 1, accumulated in S1
-                const double2* b = bk.acquire((r * 2 + c) * NP + 1) + t;
-                const bool first = (c == 0 && r == 0);
-#pragma unroll
-                for (int e = 0; e < 16; e++) {
-                    double2 sv = first ? make_double2(0.0, 0.0) : S1[e * 64 + t];
-                    cmac(sv, a[e & 7], BK::load(b + e * 64));
-                    S1[e * 64 + t] = sv;
-                }
+                        cmac(NP == 1 ? o[sp][0][q] : o[half][sp % NP][q], a[q], BK::load(b + (sp * 8 + q) * 64));
                 bk.release();
             }
         }
@@ -170,11 +155,7 @@ __device__ __forceinline__ void extern_product_step(int32_t* acc, int abar, BK& 
     group_sync(bar_id);
 #pragma unroll
     for (int c2 = 0; c2 < 2; c2++) {
-        double2 (&oc)[NP][8] = o[CR == 1 ? 0 : c2];
-        if (CR == 1 && c2 == 1) {
-#pragma unroll
-            for (int e = 0; e < NP * 8; e++) oc[e >> 3][e & 7] = S1[e * 64 + t];
-        }
+        double2 (&oc)[NP][8] = o[c2];
         uint32_t rl[8], rh[8];
 #pragma unroll
         for (int pc = 0; pc < NP; pc++) {
@@ -206,7 +187,6 @@ __global__ void __launch_bounds__(64) extern_product_kernel(const double2* __res
                                                             int32_t* __restrict__ out) {
     __shared__ double2 X1[512];
     __shared__ double2 X2[512];
-    __shared__ double2 S1[NP == 2 ? NP * kSpectrum : 1];
     __shared__ int32_t acc[2 * kN];
     const int t = threadIdx.x;
     Twiddles w; w.load(E, t);
@@ -215,7 +195,7 @@ __global__ void __launch_bounds__(64) extern_product_kernel(const double2* __res
     __syncthreads();
     const size_t row = (size_t)L * 2 * 2 * NP * kSpectrum;
     BkFromGlobal bk{bk_fft + (size_t)bk_index[g] * row};
-    extern_product_step<L, BGBIT, NP, false, false>(acc, 0, bk, w, X1, X2, S1, t, 0);
+    extern_product_step<L, BGBIT, NP, false, false>(acc, 0, bk, w, X1, X2, t, 0);
     for (int x = t; x < 2 * kN; x += 64) out[g * 2 * kN + x] = acc[x];
 }
 
@@ -290,9 +270,13 @@ struct KeyswitchArgs {
     long long in_b_offset;   // position of the input b (b_mode 0)
 };
 
-__global__ void keyswitch_kernel(KeyswitchArgs A) {
+// (A 16-ciphertexts-per-CTA lockstep variant that shares table rows through L1 cut L2 traffic 4x but executed
+// 2.4x more instructions and was slower, 18.0 vs 15.0 ms per 16 384 ciphertexts; this version runs at the L2
+// bandwidth limit, 13.8 TB/s — profiles/r1/ncu_v3_keyswitch.txt.)
+__global__ void keyswitch_kernel(KeyswitchArgs A, unsigned long long count) {
     extern __shared__ int32_t s_a[];
     const size_t g = blockIdx.x;
+    if (g >= count) return;
     const int32_t* in = A.in + g * A.in_stride + A.in_offset;
     const uint32_t prec = 1u << (32 - (1 + A.basebit * A.t));   // keyswitch.jl:58
     for (int i = threadIdx.x; i < A.Nk; i += blockDim.x) s_a[i] = (int32_t)((uint32_t)in[i] + prec);
