@@ -131,7 +131,7 @@ __device__ __forceinline__ void extern_product_step_tmem(int32_t* acc, int abar,
             double2 a[8];
 #pragma unroll
             for (int m = 0; m < 8; m++)
-                a[m] = make_double2((double)digit<BGBIT>(tl[m], r), -(double)digit<BGBIT>(th[m], r));   // tgsw.jl:104-116
+                a[m] = make_double2(digit_f64<BGBIT>(tl[m], r), -digit_f64<BGBIT>(th[m], r));   // tgsw.jl:104-116
             fft512_forward(a, w, X1, X2, t, bar_id);
             const bool first = (c == 0 && r == 0);
             if (!first) tmem_wait_st();   // this thread's previous accumulator stores have landed
@@ -168,7 +168,7 @@ __device__ __forceinline__ void extern_product_step_tmem(int32_t* acc, int abar,
             fft512_inverse(o, w, X1, X2, t, bar_id);
 #pragma unroll
             for (int m = 0; m < 8; m++) {
-                uint32_t vl = round_to_u32(o[m].x), vh = round_to_u32(-o[m].y);                       // polynomials.jl:115-116
+                uint32_t vl = round_to_u32_fast<NP == 2>(o[m].x), vh = round_to_u32_fast<NP == 2>(-o[m].y);                      // polynomials.jl:115-116
                 if (pc == 0) { rl[m] = vl; rh[m] = vh; }
                 else { rl[m] += vl << 16; rh[m] += vh << 16; }
             }

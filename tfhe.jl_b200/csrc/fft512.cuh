@@ -173,4 +173,19 @@ __device__ __forceinline__ void fft512_inverse(double2 (&a)[8], const Twiddles& 
 // round-to-nearest-even to a 64-bit integer, keep the low 32 bits (polynomials.jl:115-116)
 __device__ __forceinline__ uint32_t round_to_u32(double x) { return (uint32_t)(unsigned long long)__double2ll_rn(x); }
 
+// The same rounding for |x| < 2^51 with one FP64 add instead of F2I.S64 (a quarter-rate conversion: 14/clk/SM
+// measured, profiles/r1/microbench.json): x + 1.5*2^52 is rounded to nearest-even by the adder and the low
+// mantissa word is round(x) mod 2^32.  PROVEN == true (split transform) bounds |x| by 2^41, so it is exact;
+// the unsplit transform has no such bound and keeps the conversion instruction.
+template <bool PROVEN> __device__ __forceinline__ uint32_t round_to_u32_fast(double x) {
+    if (PROVEN) return (uint32_t)__double2loint(x + 6755399441055744.0);
+    return round_to_u32(x);
+}
+
+// digit value (an integer in [0, 2^21)) minus `half`, as a double, without I2F: 2^52 + u has u in its low
+// mantissa word, and subtracting (2^52 + half) is exact.
+__device__ __forceinline__ double small_uint_minus_half_to_double(uint32_t u, int half) {
+    return __hiloint2double(0x43300000, (int)u) - (4503599627370496.0 + (double)half);
+}
+
 }  // namespace tfhe_b200

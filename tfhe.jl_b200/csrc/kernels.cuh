@@ -39,6 +39,11 @@ template <int BGBIT> __device__ __forceinline__ int32_t digit(uint32_t x_plus_of
     return (int32_t)((x_plus_offset >> (32 - (r + 1) * BGBIT)) & ((1u << BGBIT) - 1)) - (1 << (BGBIT - 1));
 }
 
+// the same digit as a double (no integer-to-float conversion instruction, see fft512.cuh)
+template <int BGBIT> __device__ __forceinline__ double digit_f64(uint32_t x_plus_offset, int r) {
+    return small_uint_minus_half_to_double((x_plus_offset >> (32 - (r + 1) * BGBIT)) & ((1u << BGBIT) - 1), 1 << (BGBIT - 1));
+}
+
 // decode_message(x, 2N) (numeric-functions.jl:31-34) for 2N = 2048: (x + 2^20) >> 21, arithmetic
 __device__ __forceinline__ int32_t modswitch2048(int32_t x) { return (int32_t)((uint32_t)x + (1u << 20)) >> 21; }
 
@@ -136,7 +141,7 @@ __device__ __forceinline__ void extern_product_step(int32_t* acc, int abar, BK& 
             double2 a[8];
 #pragma unroll
             for (int m = 0; m < 8; m++)
-                a[m] = make_double2((double)digit<BGBIT>(tl[m], r), -(double)digit<BGBIT>(th[m], r));
+                a[m] = make_double2(digit_f64<BGBIT>(tl[m], r), -digit_f64<BGBIT>(th[m], r));
             fft512_forward(a, w, X1, X2, t, bar_id);
 #pragma unroll
             for (int half = 0; half < NP; half++) {
@@ -162,7 +167,7 @@ __device__ __forceinline__ void extern_product_step(int32_t* acc, int abar, BK& 
             fft512_inverse(oc[pc], w, X1, X2, t, bar_id);
 #pragma unroll
             for (int m = 0; m < 8; m++) {
-                uint32_t vl = round_to_u32(oc[pc][m].x), vh = round_to_u32(-oc[pc][m].y);
+                uint32_t vl = round_to_u32_fast<NP == 2>(oc[pc][m].x), vh = round_to_u32_fast<NP == 2>(-oc[pc][m].y);
                 if (pc == 0) { rl[m] = vl; rh[m] = vh; }
                 else { rl[m] += vl << 16; rh[m] += vh << 16; }
             }
@@ -248,8 +253,8 @@ __global__ void __launch_bounds__(64) polymul_kernel(const int32_t* __restrict__
     int32_t* o = out + (size_t)blockIdx.x * kN;
 #pragma unroll
     for (int m = 0; m < 8; m++) {
-        o[t + 64 * m] = (int32_t)(round_to_u32(p1[m].x) + (round_to_u32(p2[m].x) << 16));
-        o[t + 64 * m + 512] = (int32_t)(round_to_u32(-p1[m].y) + (round_to_u32(-p2[m].y) << 16));
+        o[t + 64 * m] = (int32_t)(round_to_u32_fast<true>(p1[m].x) + (round_to_u32_fast<true>(p2[m].x) << 16));
+        o[t + 64 * m + 512] = (int32_t)(round_to_u32_fast<true>(-p1[m].y) + (round_to_u32_fast<true>(-p2[m].y) << 16));
     }
 }
 

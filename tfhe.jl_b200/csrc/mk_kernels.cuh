@@ -42,7 +42,7 @@ __device__ __forceinline__ void finish_poly(double2 (&o)[NP][8], int32_t* p, con
         fft512_inverse(o[pc], w, X1, X2, t, bar_id);
 #pragma unroll
         for (int m = 0; m < 8; m++) {
-            uint32_t vl = round_to_u32(o[pc][m].x), vh = round_to_u32(-o[pc][m].y);
+            uint32_t vl = round_to_u32_fast<NP == 2>(o[pc][m].x), vh = round_to_u32_fast<NP == 2>(-o[pc][m].y);
             if (pc == 0) { rl[m] = vl; rh[m] = vh; }
             else { rl[m] += vl << 16; rh[m] += vh << 16; }
         }
@@ -95,7 +95,7 @@ __device__ __forceinline__ void mk_extern_product_step(int32_t* acc, int p, int 
             double2 a[8];
 #pragma unroll
             for (int m = 0; m < 8; m++)
-                a[m] = make_double2((double)digit<BGBIT>(tl[m], r), -(double)digit<BGBIT>(th[m], r));   // :356-357
+                a[m] = make_double2(digit_f64<BGBIT>(tl[m], r), -digit_f64<BGBIT>(th[m], r));   // :356-357
             fft512_forward(a, w, X1, X2, t, bar_id);                                                    // :368-369
             if (q < p) {
                 mac_spectrum<NP>(A, a, sample + (size_t)mk_yi(L, p, r, q) * PS, t);                     // :375-376
