@@ -198,7 +198,7 @@ struct BlindRotateArgs {
 };
 
 // per-group shared memory: X1 + X2 + acc (+ bara, n_pad words)
-__host__ __device__ constexpr int group_smem_bytes(int /*NP*/) { return 2 * kSpectrum * 16 + 2 * kN * 4; }
+__host__ __device__ constexpr int group_smem_bytes(int /*NP*/) { return (kSpectrum + kX2Elems) * 16 + 2 * kN * 4; }
 __host__ __device__ constexpr size_t br_smem_bytes(int NP, int G, int STAGES, int n_pad) {
     return (size_t)STAGES * kChunkBytes + 128 + (size_t)G * (group_smem_bytes(NP) + n_pad * 4);
 }
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs
     unsigned char* base = groups + (size_t)grp * (group_smem_bytes(NP) + A.n_pad * 4);
     double2* X1 = reinterpret_cast<double2*>(base);
     double2* X2 = X1 + kSpectrum;
-    int32_t* acc = reinterpret_cast<int32_t*>(X2 + kSpectrum);
+    int32_t* acc = reinterpret_cast<int32_t*>(X2 + kX2Elems);
     int32_t* bara = acc + 2 * kN;
     const unsigned long long g = (unsigned long long)blockIdx.x * G + grp;
     const bool valid = g < A.count;   // a group without a gate still walks the ring (on zeros) to keep the lockstep

@@ -35,6 +35,8 @@ constexpr int kN = 1024;          // polynomial degree (all parameter sets of th
 constexpr int kHalf = 512;        // complex points per transform
 constexpr int kGroup = 64;        // threads per transform
 constexpr int kSpectrum = 512;    // double2 per stored spectrum
+constexpr int kX2Elems = 576;     // double2 in the second exchange buffer: 8 rows of 8x8 tiles padded to 9x8 (conflict-free
+                                  // transposes with compile-time offsets instead of an XOR swizzle)
 
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
@@ -128,10 +130,10 @@ __device__ __forceinline__ void fft512_forward(double2 (&a)[8], const Twiddles& 
         a[5] = cmul(a[5], v5); a[6] = cmul(a[6], v6); a[7] = cmul(a[7], v7);
     }
 #pragma unroll
-    for (int q2 = 0; q2 < 8; q2++) X2[hi * 64 + q2 * 8 + (lo ^ q2)] = a[q2];
+    for (int q2 = 0; q2 < 8; q2++) X2[hi * 72 + q2 * 9 + lo] = a[q2];
     group_sync(bar_id);
 #pragma unroll
-    for (int t1 = 0; t1 < 8; t1++) a[t1] = X2[hi * 64 + lo * 8 + (t1 ^ lo)];
+    for (int t1 = 0; t1 < 8; t1++) a[t1] = X2[hi * 72 + lo * 9 + t1];
     dft8<false>(a);
 }
 
@@ -147,10 +149,10 @@ __device__ __forceinline__ void fft512_inverse(double2 (&a)[8], const Twiddles& 
         a[5] = cmulc(a[5], v5); a[6] = cmulc(a[6], v6); a[7] = cmulc(a[7], v7);
     }
 #pragma unroll
-    for (int t1 = 0; t1 < 8; t1++) X2[hi * 64 + lo * 8 + (t1 ^ lo)] = a[t1];
+    for (int t1 = 0; t1 < 8; t1++) X2[hi * 72 + lo * 9 + t1] = a[t1];
     group_sync(bar_id);
 #pragma unroll
-    for (int q2 = 0; q2 < 8; q2++) a[q2] = X2[hi * 64 + q2 * 8 + (lo ^ q2)];
+    for (int q2 = 0; q2 < 8; q2++) a[q2] = X2[hi * 72 + q2 * 9 + lo];
     dft8<true>(a);   // q2 -> t2
 #pragma unroll
     for (int t2 = 0; t2 < 8; t2++) X1[hi * 64 + lo + 8 * t2] = a[t2];

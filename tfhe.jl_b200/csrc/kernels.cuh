@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(64) bk_transform_kernel(const int32_t* __restr
                                                           double2* __restrict__ out,
                                                           const double2* __restrict__ E) {
     __shared__ double2 X1[512];
-    __shared__ double2 X2[512];
+    __shared__ double2 X2[kX2Elems];
     const int t = threadIdx.x;
     Twiddles w; w.load(E, t);
     const int32_t* p = polys + (size_t)blockIdx.x * kN;
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(64) extern_product_kernel(const double2* __res
                                                             const int32_t* __restrict__ bk_index,
                                                             int32_t* __restrict__ out) {
     __shared__ double2 X1[512];
-    __shared__ double2 X2[512];
+    __shared__ double2 X2[kX2Elems];
     __shared__ int32_t acc[2 * kN];
     const int t = threadIdx.x;
     Twiddles w; w.load(E, t);
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(64) extern_product_kernel(const double2* __res
 __global__ void __launch_bounds__(64) polymul_kernel(const int32_t* __restrict__ xs, const int32_t* __restrict__ ys,
                                                      int32_t* __restrict__ out, const double2* __restrict__ E) {
     __shared__ double2 X1[512];
-    __shared__ double2 X2[512];
+    __shared__ double2 X2[kX2Elems];
     __shared__ double2 SX[2][512];   // spectra of xl, xh
     const int t = threadIdx.x;
     Twiddles w; w.load(E, t);

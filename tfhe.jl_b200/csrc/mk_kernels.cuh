@@ -142,7 +142,7 @@ struct MKBlindRotateArgs {
 };
 
 __host__ __device__ inline size_t mk_smem_bytes(int p, int n, int NP) {
-    return (size_t)2 * kSpectrum * 16 + (size_t)NP * kSpectrum * 16 + (size_t)(p + 1) * kN * 4 + (size_t)((p * n + 3) & ~3) * 4;
+    return (size_t)(kSpectrum + kX2Elems) * 16 + (size_t)NP * kSpectrum * 16 + (size_t)(p + 1) * kN * 4 + (size_t)((p * n + 3) & ~3) * 4;
 }
 
 template <int L, int BGBIT, int NP>
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(64) mk_blind_rotate_kernel(MKBlindRotateArgs M
     const int t = threadIdx.x, p = M.p, n = M.n;
     double2* X1 = reinterpret_cast<double2*>(smem_raw);
     double2* X2 = X1 + kSpectrum;
-    double2* S = X2 + kSpectrum;
+    double2* S = X2 + kX2Elems;
     int32_t* acc = reinterpret_cast<int32_t*>(S + NP * kSpectrum);
     int32_t* bara = acc + (p + 1) * kN;
     const size_t g = blockIdx.x;
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(64) mk_extern_product_kernel(const double2* __
     const int t = threadIdx.x;
     double2* X1 = reinterpret_cast<double2*>(smem_raw);
     double2* X2 = X1 + kSpectrum;
-    double2* S = X2 + kSpectrum;
+    double2* S = X2 + kX2Elems;
     int32_t* acc = reinterpret_cast<int32_t*>(S + NP * kSpectrum);
     const size_t g = blockIdx.x;
     Twiddles w; w.load(E, t);
