@@ -111,11 +111,19 @@ template <int L, int NP, int STAGES> struct BkFromRing {
 // read-modify-write of the accumulators runs on the TMEM datapath (LDTM/STTM), off the shared-memory pipe.
 // `tm` is the TMEM address of this thread's row (lane and first column already applied); the accumulator of
 // output component c2, piece pc occupies columns [(c2*NP + pc)*32, +32).
-template <int L, int BGBIT, int NP, class BK>
+// REGH = 1 (NP == 2 only): the two pieces of output component 0 stay in registers (64 registers) and only
+// component 1 goes through TMEM, which halves the TMEM round trips.
+template <int L, int BGBIT, int NP, int REGH, class BK>
 __device__ __forceinline__ void extern_product_step_tmem(int32_t* acc, int abar, BK& bk, const Twiddles& w, double2* X1,
                                                          double2* X2, uint32_t tm, int t, int bar_id) {
+    static_assert(REGH == 0 || NP == 2, "REGH needs the two-piece transform");
     constexpr uint32_t offset = decomp_offset<L, BGBIT>();
     const int s = abar & 2047;
+    double2 oreg[REGH ? 2 : 1][8];
+#pragma unroll
+    for (int sp = 0; sp < (REGH ? 2 : 1); sp++)
+#pragma unroll
+        for (int q = 0; q < 8; q++) oreg[sp][q] = make_double2(0.0, 0.0);
 #pragma unroll 1
     for (int c = 0; c < 2; c++) {
         const int32_t* p = acc + c * kN;
@@ -140,6 +148,11 @@ __device__ __forceinline__ void extern_product_step_tmem(int32_t* acc, int abar,
                 const double2* b = bk.acquire((r * 2 + c) * NP + half) + t;
 #pragma unroll
                 for (int sp = 0; sp < 2; sp++) {
+                    if (REGH && half == 0) {
+#pragma unroll
+                        for (int q = 0; q < 8; q++) cmac(oreg[sp][q], a[q], BK::load(b + (sp * 8 + q) * 64));
+                        continue;
+                    }
                     const uint32_t col = tm + (uint32_t)((NP == 1 ? sp : half * 2 + sp) * 32);
                     double2 o[8];
                     if (first) {
@@ -158,13 +171,18 @@ __device__ __forceinline__ void extern_product_step_tmem(int32_t* acc, int abar,
     }
     tmem_wait_st();
     group_sync(bar_id);   // all reads of acc and of X2 (last forward) are done
-#pragma unroll 1
+#pragma unroll
     for (int c2 = 0; c2 < 2; c2++) {
         uint32_t rl[8], rh[8];
 #pragma unroll
         for (int pc = 0; pc < NP; pc++) {
             double2 o[8];
-            tmem_load_spectrum(tm + (uint32_t)((c2 * NP + pc) * 32), o);
+            if (REGH && c2 == 0) {
+#pragma unroll
+                for (int q = 0; q < 8; q++) o[q] = oreg[pc % 2][q];
+            } else {
+                tmem_load_spectrum(tm + (uint32_t)((c2 * NP + pc) * 32), o);
+            }
             fft512_inverse(o, w, X1, X2, t, bar_id);
 #pragma unroll
             for (int m = 0; m < 8; m++) {
@@ -211,7 +229,7 @@ __host__ __device__ constexpr int br_tmem_cols(int NP, int G) {
     return c;
 }
 
-template <int L, int BGBIT, int NP, int G, int STAGES, int MODE, bool TM = false>
+template <int L, int BGBIT, int NP, int G, int STAGES, int MODE, int TM = 0>
 __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t s_tmem_base;
@@ -281,7 +299,7 @@ __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs
 
 #pragma unroll 1
     for (int i = 0; i < A.n_iter; i++) {   // bootstrap.jl:19-23
-        if (TM) extern_product_step_tmem<L, BGBIT, NP>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id);
+        if (TM) extern_product_step_tmem<L, BGBIT, NP, (TM == 2 && NP == 2) ? 1 : 0>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id);
         else extern_product_step<L, BGBIT, NP, true, true>(acc, bara[i], bk, w, X1, X2, t, bar_id);
     }
 

@@ -84,7 +84,7 @@ int env_int(const char* name, int dflt) {
 }
 
 // ---- kernel dispatch ------------------------------------------------------------------------------
-template <int L, int BGBIT, int NP, int G, int STAGES, int MODE, bool TM = false>
+template <int L, int BGBIT, int NP, int G, int STAGES, int MODE, int TM = 0>
 int launch_br_g(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
     auto kern = blind_rotate_kernel<L, BGBIT, NP, G, STAGES, MODE, TM>;
     const size_t smem = br_smem_bytes(NP, G, STAGES, A.n_pad);
@@ -105,16 +105,16 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
     } else {
         // 4 gates = 8 warps = 2 per SM sub-partition: the only shape that leaves 255 registers per thread
         switch (ctx->G) {
-            case 104: return launch_br_g<L, BGBIT, NP, 4, 6, MODE, true>(ctx, A, s);   // TMEM accumulators
-            case 105: return launch_br_g<L, BGBIT, NP, 5, 4, MODE, true>(ctx, A, s);
-            case 106: return launch_br_g<L, BGBIT, NP, 6, 3, MODE, true>(ctx, A, s);
-            case 107: return launch_br_g<L, BGBIT, NP, 7, 2, MODE, true>(ctx, A, s);
+            case 104: return launch_br_g<L, BGBIT, NP, 4, 6, MODE, 1>(ctx, A, s);   // all accumulators in TMEM
+            case 106: return launch_br_g<L, BGBIT, NP, 6, 3, MODE, 1>(ctx, A, s);
+            case 204: return launch_br_g<L, BGBIT, NP, 4, 6, MODE, 2>(ctx, A, s);   // component 0 in registers, component 1 in TMEM
             case 4: return launch_br_g<L, BGBIT, NP, 4, 6, MODE>(ctx, A, s);           // register accumulators
             default:
                 // measured (profiles/r1): with one 32-bit piece the 64 accumulator registers fit and registers win
-                // (142 k vs 135 k gates/s); with two pieces (128 registers) TMEM wins (96 k vs 88 k gates/s)
+                // (148 k vs 135 k gates/s); with two pieces (128 registers) the fastest is component 0 in registers
+                // and component 1 in TMEM (102 k; all in TMEM 98 k; all in registers, 72 B of spills, 88 k gates/s)
                 if constexpr (NP == 1) return launch_br_g<L, BGBIT, NP, 4, 6, MODE>(ctx, A, s);
-                else return launch_br_g<L, BGBIT, NP, 4, 6, MODE, true>(ctx, A, s);
+                else return launch_br_g<L, BGBIT, NP, 4, 6, MODE, 2>(ctx, A, s);
         }
     }
 }
