@@ -140,19 +140,28 @@ __device__ __forceinline__ void extern_product_step_tmem(int32_t* acc, int abar,
 #pragma unroll
             for (int m = 0; m < 8; m++)
                 a[m] = make_double2(digit_f64<BGBIT>(tl[m], r), -digit_f64<BGBIT>(th[m], r));   // tgsw.jl:104-116
-            fft512_forward(a, w, X1, X2, t, bar_id);
+            double2 kv[REGH ? 16 : 1];
+            fft512_forward(a, w, X1, X2, t, bar_id, [&]() {
+                if (REGH) {   // first key chunk of (r, c) loaded behind the transform's last exchange
+                    const double2* b = bk.acquire((r * 2 + c) * NP) + t;
+#pragma unroll
+                    for (int e = 0; e < 16; e++) kv[e % (REGH ? 16 : 1)] = BK::load(b + e * 64);
+                }
+            });
             const bool first = (c == 0 && r == 0);
             if (!first) tmem_wait_st();   // this thread's previous accumulator stores have landed
+            if (REGH) {
 #pragma unroll
-            for (int half = 0; half < NP; half++) {
+                for (int sp = 0; sp < 2; sp++)
+#pragma unroll
+                    for (int q = 0; q < 8; q++) cmac(oreg[sp][q], a[q], kv[(sp * 8 + q) % (REGH ? 16 : 1)]);
+                bk.release();
+            }
+#pragma unroll
+            for (int half = REGH ? 1 : 0; half < NP; half++) {
                 const double2* b = bk.acquire((r * 2 + c) * NP + half) + t;
 #pragma unroll
                 for (int sp = 0; sp < 2; sp++) {
-                    if (REGH && half == 0) {
-#pragma unroll
-                        for (int q = 0; q < 8; q++) cmac(oreg[sp][q], a[q], BK::load(b + (sp * 8 + q) * 64));
-                        continue;
-                    }
                     const uint32_t col = tm + (uint32_t)((NP == 1 ? sp : half * 2 + sp) * 32);
                     double2 o[8];
                     if (first) {

@@ -106,8 +106,13 @@ struct Twiddles {
 
 // Forward transform.  In: a[m] = z_{t+64m} (untwisted).  Out: a[q3] = Z_{q + 8*q2 + 64*q3}, v = q2 + 8q = t.
 // X1, X2: two 512-element double2 scratch buffers private to the 64-thread group.
+struct NoPrefetch { __device__ __forceinline__ void operator()() const {} };
+
+// `prefetch` runs right after the second barrier, before the X2 loads are issued: callers use it to put
+// further shared-memory loads (the key chunk of the multiply-accumulate) in flight behind the same wait.
+template <class F = NoPrefetch>
 __device__ __forceinline__ void fft512_forward(double2 (&a)[8], const Twiddles& w, double2* X1, double2* X2, int t,
-                                               int bar_id) {
+                                               int bar_id, F&& prefetch = F()) {
 #pragma unroll
     for (int m = 1; m < 8; m++) a[m] = cmul(a[m], make_double2(kTwistRe[m], kTwistIm[m]));
     dft8<false>(a);
@@ -132,6 +137,7 @@ __device__ __forceinline__ void fft512_forward(double2 (&a)[8], const Twiddles& 
 #pragma unroll
     for (int q2 = 0; q2 < 8; q2++) X2[hi * 72 + q2 * 9 + lo] = a[q2];
     group_sync(bar_id);
+    prefetch();
 #pragma unroll
     for (int t1 = 0; t1 < 8; t1++) a[t1] = X2[hi * 72 + lo * 9 + t1];
     dft8<false>(a);
