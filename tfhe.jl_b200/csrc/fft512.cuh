@@ -15,7 +15,7 @@
 //           T_q(t) = E(t*(4q+1)), E(x) = exp(-i*pi*x/1024).
 //   exchange 1 (X1): (t1,t2 | q) -> thread t1 + 8q, register t2          [t = t1 + 8*t2]
 //   pass 2: radix-8 over t2 -> q2, twiddle W64^(t1*q2) = E(32*t1*q2)
-//   exchange 2 (X2): (t1,q | q2) -> thread q2 + 8q, register t1          [XOR swizzle, conflict-free]
+//   exchange 2 (X2): (t1,q | q2) -> thread q2 + 8q, register t1          [8x8 tiles padded to 9x8: conflict-free]
 //   pass 3: radix-8 over t1 -> q3
 //
 // Output: thread v = q2 + 8q, register q3 holds frequency k = q + 8*q2 + 64*q3.  The transform-domain
