@@ -249,6 +249,12 @@ def main():
 
         reps = max(1, min(args.steps, 3))
         br_ms, ks_ms = kernel_ms(br_only, reps), kernel_ms(ks_only, reps)
+
+        # the second half of BASELINE.json's metric: latency of ONE bootstrapped gate (device-resident operands)
+        def one_gate():
+            ctx.gate_dev(O.NAND, dx.data_ptr(), dy.data_ptr(), 0, dout.data_ptr(), 1, stream=stream)
+
+        lat = sorted(kernel_ms(one_gate, 1) for _ in range(9))[4]
         fp64_peak = ctx.measure_fp64_tflops()
         achieved = W_FFT_FLOP_PER_GATE * B / (br_ms * 1e-3) / 1e12
         peaks = {}
@@ -269,8 +275,10 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "gates/s", "h2d_bytes_per_step": 2 * B * W * 4 * world, "d2h_bytes_per_step": B * W * 4 * world},
             "gpu_launches": int(launches),
+            "single_bootstrap_latency_ms": lat,
             "roofline": {"bound": "fp64", "kernel": "blind_rotate_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak, "traffic": None,
+                         "traffic_note": "ncu --set full on a 4096-gate launch: dram read 304 MB + write 20 MB (profiles/r1/ncu_v5_blind_rotate_split.txt); keys are L2-resident, the kernel is not DRAM-bound",
                          "peak_source": "FP64 FMA rate measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry); not tensor- or HBM-bound: keys are L2-resident",
                          "kernel_ms": br_ms, "algorithmic_flop_per_gate": W_FFT_FLOP_PER_GATE, "share_of_step": br_ms / (ms_total / args.steps)},
             "roofline_keyswitch": {"bound": "hbm", "kernel": "keyswitch_kernel", "achieved": ks_gbs, "peak": hbm_peak, "unit": "GB/s",

@@ -211,115 +211,6 @@ __device__ __forceinline__ void extern_product_step_tmem(int32_t* acc, int abar,
     group_sync(bar_id);
 }
 
-// K2 with the transforms done two at a time (fft512_forward_dual / fft512_inverse_dual): the digit polynomials
-// r, r+1 of one accumulator component go forward together, and the inverse runs on the two output components
-// (NP == 1) or on the two 16-bit pieces of one component (NP == 2) together.  Accumulators: NP == 1 both
-// components in registers; NP == 2 component 0 in registers, component 1 in TMEM (columns [0,32) lo, [32,64) hi).
-template <int L, int BGBIT, int NP, class BK>
-__device__ __forceinline__ void extern_product_step_dual(int32_t* acc, int abar, BK& bk, const Twiddles& w,
-                                                         const ExchangeBuffers& X, uint32_t tm, int t, int bar_id) {
-    constexpr uint32_t offset = decomp_offset<L, BGBIT>();
-    const int s = abar & 2047;
-    double2 o[2][8];   // NP == 1: output components 0, 1;  NP == 2: pieces lo, hi of output component 0
-#pragma unroll
-    for (int sp = 0; sp < 2; sp++)
-#pragma unroll
-        for (int q = 0; q < 8; q++) o[sp][q] = make_double2(0.0, 0.0);
-
-    auto mac = [&](const double2 (&a)[8], int r, int c, bool first) {
-        {
-            const double2* b = bk.acquire((r * 2 + c) * NP) + t;
-#pragma unroll
-            for (int sp = 0; sp < 2; sp++)
-#pragma unroll
-                for (int q = 0; q < 8; q++) cmac(o[sp][q], a[q], BK::load(b + (sp * 8 + q) * 64));   // tgsw.jl:128
-            bk.release();
-        }
-        if (NP == 2) {
-            const double2* b = bk.acquire((r * 2 + c) * NP + 1) + t;
-            if (!first) tmem_wait_st();
-#pragma unroll
-            for (int sp = 0; sp < 2; sp++) {
-                double2 v[8];
-                if (first) {
-#pragma unroll
-                    for (int q = 0; q < 8; q++) v[q] = make_double2(0.0, 0.0);
-                } else {
-                    tmem_load_spectrum(tm + sp * 32, v);
-                }
-#pragma unroll
-                for (int q = 0; q < 8; q++) cmac(v[q], a[q], BK::load(b + (sp * 8 + q) * 64));
-                tmem_store_spectrum(tm + sp * 32, v);
-            }
-            bk.release();
-        }
-    };
-
-#pragma unroll 1
-    for (int c = 0; c < 2; c++) {
-        const int32_t* p = acc + c * kN;
-        uint32_t tl[8], th[8];
-#pragma unroll
-        for (int m = 0; m < 8; m++) {
-            int j = t + 64 * m;
-            tl[m] = (uint32_t)rot_coeff(p, j, s) - (uint32_t)p[j] + offset;                 // bootstrap.jl:21
-            th[m] = (uint32_t)rot_coeff(p, j + 512, s) - (uint32_t)p[j + 512] + offset;
-        }
-#pragma unroll
-        for (int r = 0; r < L; r += 2) {
-            double2 a0[8], a1[8];
-#pragma unroll
-            for (int m = 0; m < 8; m++) a0[m] = make_double2(digit_f64<BGBIT>(tl[m], r), -digit_f64<BGBIT>(th[m], r));
-            if (r + 1 < L) {
-#pragma unroll
-                for (int m = 0; m < 8; m++)
-                    a1[m] = make_double2(digit_f64<BGBIT>(tl[m], r + 1), -digit_f64<BGBIT>(th[m], r + 1));
-                fft512_forward_dual(a0, a1, w, X, t, bar_id);
-                mac(a0, r, c, c == 0 && r == 0);
-                mac(a1, r + 1, c, false);
-            } else {
-                fft512_forward(a0, w, X.X1a, X.X2a, t, bar_id);
-                mac(a0, r, c, c == 0 && r == 0);
-            }
-        }
-    }
-    if (NP == 2) tmem_wait_st();
-    group_sync(bar_id);   // all reads of acc and of the X2 buffers (last forward) are done
-
-    auto add_into = [&](int32_t* p, const uint32_t (&rl)[8], const uint32_t (&rh)[8]) {
-#pragma unroll
-        for (int m = 0; m < 8; m++) {
-            int j = t + 64 * m;
-            p[j] = (int32_t)((uint32_t)p[j] + rl[m]);                                               // bootstrap.jl:22
-            p[j + 512] = (int32_t)((uint32_t)p[j + 512] + rh[m]);
-        }
-    };
-    if (NP == 1) {
-        fft512_inverse_dual(o[0], o[1], w, X, t, bar_id);
-#pragma unroll
-        for (int c2 = 0; c2 < 2; c2++) {
-            uint32_t rl[8], rh[8];
-#pragma unroll
-            for (int m = 0; m < 8; m++) { rl[m] = round_to_u32(o[c2][m].x); rh[m] = round_to_u32(-o[c2][m].y); }   // polynomials.jl:115-116
-            add_into(acc + c2 * kN, rl, rh);
-        }
-    } else {
-#pragma unroll
-        for (int c2 = 0; c2 < 2; c2++) {
-            if (c2 == 1) { tmem_load_spectrum(tm, o[0]); tmem_load_spectrum(tm + 32, o[1]); }
-            fft512_inverse_dual(o[0], o[1], w, X, t, bar_id);
-            uint32_t rl[8], rh[8];
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                rl[m] = round_to_u32_fast<true>(o[0][m].x) + (round_to_u32_fast<true>(o[1][m].x) << 16);
-                rh[m] = round_to_u32_fast<true>(-o[0][m].y) + (round_to_u32_fast<true>(-o[1][m].y) << 16);
-            }
-            add_into(acc + c2 * kN, rl, rh);
-        }
-    }
-    group_sync(bar_id);
-}
-
 struct BlindRotateArgs {
     const double2* bk_fft;   // [n][L][2][2][NP][512]
     const double2* E;        // twiddle table, 2048 entries
@@ -334,12 +225,9 @@ struct BlindRotateArgs {
 };
 
 // per-group shared memory: X1 + X2 + acc (+ bara, n_pad words)
-// (TM == 3, the two-transforms-at-a-time step, needs two sets of exchange buffers)
-__host__ __device__ constexpr int group_smem_bytes(int /*NP*/, int TM = 0) {
-    return (TM == 3 ? 2 : 1) * (kSpectrum + kX2Elems) * 16 + 2 * kN * 4;
-}
-__host__ __device__ constexpr size_t br_smem_bytes(int NP, int G, int STAGES, int n_pad, int TM = 0) {
-    return (size_t)STAGES * kChunkBytes + 128 + (size_t)G * (group_smem_bytes(NP, TM) + n_pad * 4);
+__host__ __device__ constexpr int group_smem_bytes(int /*NP*/) { return (kSpectrum + kX2Elems) * 16 + 2 * kN * 4; }
+__host__ __device__ constexpr size_t br_smem_bytes(int NP, int G, int STAGES, int n_pad) {
+    return (size_t)STAGES * kChunkBytes + 128 + (size_t)G * (group_smem_bytes(NP) + n_pad * 4);
 }
 
 // TMEM columns to allocate when the accumulators live in tensor memory: warps that share a lane quarter
@@ -354,7 +242,7 @@ template <int L, int BGBIT, int NP, int G, int STAGES, int MODE, int TM = 0>
 __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t s_tmem_base;
-    constexpr bool kUseTmem = TM == 1 || TM == 2 || (TM == 3 && NP == 2);
+    constexpr bool kUseTmem = TM != 0;   // TM: 0 = accumulators in registers, 1 = all in TMEM, 2 = component 1 in TMEM
     if (kUseTmem) {
         if ((threadIdx.x >> 5) == 0) tmem_alloc<br_tmem_cols(NP, G)>(&s_tmem_base);
         tmem_fence_before_sync();
@@ -381,11 +269,10 @@ __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs
     // ---------------- consumers: one 64-thread group per gate ----------------
     const int t = threadIdx.x & 63, grp = threadIdx.x >> 6;
     const int bar_id = grp + 1;
-    unsigned char* base = groups + (size_t)grp * (group_smem_bytes(NP, TM) + A.n_pad * 4);
+    unsigned char* base = groups + (size_t)grp * (group_smem_bytes(NP) + A.n_pad * 4);
     double2* X1 = reinterpret_cast<double2*>(base);
     double2* X2 = X1 + kSpectrum;
-    const ExchangeBuffers XB{X1, X2, X2 + kX2Elems, X2 + kX2Elems + kSpectrum};   // second set only exists for TM == 3
-    int32_t* acc = reinterpret_cast<int32_t*>(X2 + kX2Elems + (TM == 3 ? kSpectrum + kX2Elems : 0));
+    int32_t* acc = reinterpret_cast<int32_t*>(X2 + kX2Elems);
     int32_t* bara = acc + 2 * kN;
     const unsigned long long g = (unsigned long long)blockIdx.x * G + grp;
     const bool valid = g < A.count;   // a group without a gate still walks the ring (on zeros) to keep the lockstep
@@ -422,8 +309,7 @@ __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs
 
 #pragma unroll 1
     for (int i = 0; i < A.n_iter; i++) {   // bootstrap.jl:19-23
-        if (TM == 3) extern_product_step_dual<L, BGBIT, NP>(acc, bara[i], bk, w, XB, tm, t, bar_id);
-        else if (TM) extern_product_step_tmem<L, BGBIT, NP, (TM == 2 && NP == 2) ? 1 : 0>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id);
+        if (TM) extern_product_step_tmem<L, BGBIT, NP, (TM == 2 && NP == 2) ? 1 : 0>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id);
         else extern_product_step<L, BGBIT, NP, true, true>(acc, bara[i], bk, w, X1, X2, t, bar_id);
     }
 

@@ -87,7 +87,7 @@ int env_int(const char* name, int dflt) {
 template <int L, int BGBIT, int NP, int G, int STAGES, int MODE, int TM = 0>
 int launch_br_g(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
     auto kern = blind_rotate_kernel<L, BGBIT, NP, G, STAGES, MODE, TM>;
-    const size_t smem = br_smem_bytes(NP, G, STAGES, A.n_pad, TM);
+    const size_t smem = br_smem_bytes(NP, G, STAGES, A.n_pad);
     if (smem > 227 * 1024) return fail(ctx, TFHE_B200_EINVAL, "LWE dimension too large for the shared-memory layout");
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned grid = (unsigned)((A.count + G - 1) / G);
@@ -108,8 +108,6 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
             case 104: return launch_br_g<L, BGBIT, NP, 4, 6, MODE, 1>(ctx, A, s);   // all accumulators in TMEM
             case 106: return launch_br_g<L, BGBIT, NP, 6, 3, MODE, 1>(ctx, A, s);
             case 204: return launch_br_g<L, BGBIT, NP, 4, 6, MODE, 2>(ctx, A, s);   // component 0 in registers, component 1 in TMEM
-            case 304: return launch_br_g<L, BGBIT, NP, 4, 3, MODE, 3>(ctx, A, s);   // two transforms at a time
-            case 303: return launch_br_g<L, BGBIT, NP, 3, 4, MODE, 3>(ctx, A, s);
             case 4: return launch_br_g<L, BGBIT, NP, 4, 6, MODE>(ctx, A, s);           // register accumulators
             default:
                 // measured (profiles/r1): with one 32-bit piece the 64 accumulator registers fit and registers win

@@ -178,90 +178,6 @@ __device__ __forceinline__ void fft512_inverse(double2 (&a)[8], const Twiddles& 
     for (int m = 1; m < 8; m++) a[m] = cmulc(a[m], make_double2(kTwistRe[m] * sc, kTwistIm[m] * sc));
 }
 
-// ---- two transforms at once ----------------------------------------------------------------------------
-// The same dataflow on two independent polynomials with ONE pair of barriers: twice the independent FP64 work
-// between dependent instructions, 16 exchange loads in flight per wait instead of 8, half the barriers, and the
-// derived twiddles are shared.  Xa/Xb are the two groups of exchange buffers (X1 at [0], X2 at [kSpectrum]).
-struct ExchangeBuffers { double2* X1a; double2* X2a; double2* X1b; double2* X2b; };
-
-template <class F = NoPrefetch>
-__device__ __forceinline__ void fft512_forward_dual(double2 (&a)[8], double2 (&b)[8], const Twiddles& w,
-                                                    const ExchangeBuffers& X, int t, int bar_id, F&& prefetch = F()) {
-#pragma unroll
-    for (int m = 1; m < 8; m++) {
-        const double2 c = make_double2(kTwistRe[m], kTwistIm[m]);
-        a[m] = cmul(a[m], c); b[m] = cmul(b[m], c);
-    }
-    dft8<false>(a); dft8<false>(b);
-    {
-        double2 T[8];
-        T[0] = w.e1; T[1] = cmul(w.e1, w.s1); T[2] = cmul(w.e1, w.s2); T[3] = cmul(T[1], w.s2); T[4] = cmul(w.e1, w.s4);
-        T[5] = cmul(T[1], w.s4); T[6] = cmul(T[2], w.s4); T[7] = cmul(T[3], w.s4);
-#pragma unroll
-        for (int q = 0; q < 8; q++) { a[q] = cmul(a[q], T[q]); b[q] = cmul(b[q], T[q]); }
-    }
-#pragma unroll
-    for (int q = 0; q < 8; q++) { X.X1a[q * 64 + t] = a[q]; X.X1b[q * 64 + t] = b[q]; }
-    group_sync(bar_id);
-    const int lo = t & 7, hi = t >> 3;
-#pragma unroll
-    for (int t2 = 0; t2 < 8; t2++) { a[t2] = X.X1a[hi * 64 + lo + 8 * t2]; b[t2] = X.X1b[hi * 64 + lo + 8 * t2]; }
-    dft8<false>(a); dft8<false>(b);
-    {
-        double2 V[8];
-        V[1] = w.v1; V[2] = w.v2; V[3] = cmul(w.v1, w.v2); V[4] = w.v4; V[5] = cmul(w.v1, w.v4); V[6] = cmul(w.v2, w.v4);
-        V[7] = cmul(V[3], w.v4);
-#pragma unroll
-        for (int q = 1; q < 8; q++) { a[q] = cmul(a[q], V[q]); b[q] = cmul(b[q], V[q]); }
-    }
-#pragma unroll
-    for (int q2 = 0; q2 < 8; q2++) { X.X2a[hi * 72 + q2 * 9 + lo] = a[q2]; X.X2b[hi * 72 + q2 * 9 + lo] = b[q2]; }
-    group_sync(bar_id);
-    prefetch();
-#pragma unroll
-    for (int t1 = 0; t1 < 8; t1++) { a[t1] = X.X2a[hi * 72 + lo * 9 + t1]; b[t1] = X.X2b[hi * 72 + lo * 9 + t1]; }
-    dft8<false>(a); dft8<false>(b);
-}
-
-__device__ __forceinline__ void fft512_inverse_dual(double2 (&a)[8], double2 (&b)[8], const Twiddles& w,
-                                                    const ExchangeBuffers& X, int t, int bar_id) {
-    const int lo = t & 7, hi = t >> 3;
-    dft8<true>(a); dft8<true>(b);
-    {
-        double2 V[8];
-        V[1] = w.v1; V[2] = w.v2; V[3] = cmul(w.v1, w.v2); V[4] = w.v4; V[5] = cmul(w.v1, w.v4); V[6] = cmul(w.v2, w.v4);
-        V[7] = cmul(V[3], w.v4);
-#pragma unroll
-        for (int q = 1; q < 8; q++) { a[q] = cmulc(a[q], V[q]); b[q] = cmulc(b[q], V[q]); }
-    }
-#pragma unroll
-    for (int t1 = 0; t1 < 8; t1++) { X.X2a[hi * 72 + lo * 9 + t1] = a[t1]; X.X2b[hi * 72 + lo * 9 + t1] = b[t1]; }
-    group_sync(bar_id);
-#pragma unroll
-    for (int q2 = 0; q2 < 8; q2++) { a[q2] = X.X2a[hi * 72 + q2 * 9 + lo]; b[q2] = X.X2b[hi * 72 + q2 * 9 + lo]; }
-    dft8<true>(a); dft8<true>(b);
-#pragma unroll
-    for (int t2 = 0; t2 < 8; t2++) { X.X1a[hi * 64 + lo + 8 * t2] = a[t2]; X.X1b[hi * 64 + lo + 8 * t2] = b[t2]; }
-    group_sync(bar_id);
-#pragma unroll
-    for (int q = 0; q < 8; q++) { a[q] = X.X1a[q * 64 + t]; b[q] = X.X1b[q * 64 + t]; }
-    {
-        double2 T[8];
-        T[0] = w.e1; T[1] = cmul(w.e1, w.s1); T[2] = cmul(w.e1, w.s2); T[3] = cmul(T[1], w.s2); T[4] = cmul(w.e1, w.s4);
-        T[5] = cmul(T[1], w.s4); T[6] = cmul(T[2], w.s4); T[7] = cmul(T[3], w.s4);
-#pragma unroll
-        for (int q = 0; q < 8; q++) { a[q] = cmulc(a[q], T[q]); b[q] = cmulc(b[q], T[q]); }
-    }
-    dft8<true>(a); dft8<true>(b);
-    constexpr double sc = 1.0 / 512.0;
-    a[0] = make_double2(a[0].x * sc, a[0].y * sc); b[0] = make_double2(b[0].x * sc, b[0].y * sc);
-#pragma unroll
-    for (int m = 1; m < 8; m++) {
-        const double2 c = make_double2(kTwistRe[m] * sc, kTwistIm[m] * sc);
-        a[m] = cmulc(a[m], c); b[m] = cmulc(b[m], c);
-    }
-}
-
 // round-to-nearest-even to a 64-bit integer, keep the low 32 bits (polynomials.jl:115-116)
 __device__ __forceinline__ uint32_t round_to_u32(double x) { return (uint32_t)(unsigned long long)__double2ll_rn(x); }
 
