@@ -213,7 +213,7 @@ class Rng:
         self.h = lib().orc_rng_create(seed)
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:
             lib().orc_rng_destroy(self.h); self.h = None
 
 
@@ -270,7 +270,7 @@ class Context:
         self.h = lib().orc_create(C.byref(cp), _p(keys.bk), _p(keys.ksk))
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:
             lib().orc_destroy(self.h); self.h = None
 
     def extern_mul(self, i, acc, route=ROUTE_EXACT):
@@ -359,7 +359,7 @@ class MKContext:
         self.h = lib().orc_mk_create(C.byref(cp), self.p, _p(keys.bk), _p(keys.ksk))
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:
             lib().orc_mk_destroy(self.h); self.h = None
 
     def extern_mul(self, party, j, acc, route=ROUTE_EXACT):

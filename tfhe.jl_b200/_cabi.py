@@ -117,7 +117,11 @@ class Context:
             lib().tfhe_b200_destroy(self._h)
             self._h = C.c_void_p()
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # interpreter shutdown: module globals may already be gone
+            pass
 
     def _ck(self, rc):
         if rc != 0:

@@ -37,6 +37,7 @@ struct tfhe_b200_ctx {
     uint32_t flags = 0;
     int NP = 2;
     int G = 0;                       // gates per CTA of the blind-rotation kernel (0 = default, see launch_br_np)
+    int sm_count = 148;
     cudaStream_t stream = nullptr;   // used by the host-buffer entry points
     double2* d_E = nullptr;          // exp(-i*pi*x/1024), x < 2048
     double2* d_bk_fft = nullptr;     // single-key: [n][l][2][2][NP][512]; MK: [p][n][l*(2p+2)][NP][512]
@@ -113,8 +114,16 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
                 // measured (profiles/r1): with one 32-bit piece the 64 accumulator registers fit and registers win
                 // (148 k vs 135 k gates/s); with two pieces (128 registers) the fastest is component 0 in registers
                 // and component 1 in TMEM (102 k; all in TMEM 98 k; all in registers, 72 B of spills, 88 k gates/s)
-                if constexpr (NP == 1) return launch_br_g<L, BGBIT, NP, 4, 6, MODE>(ctx, A, s);
-                else return launch_br_g<L, BGBIT, NP, 4, 6, MODE, 2>(ctx, A, s);
+                // Small batches (dependent circuits, single gates): fewer gates per CTA so that every gate gets an
+                // SM (sub-partition) of its own — a lone group finishes an iteration ~3x sooner than four sharing
+                // the FP64 pipe, and groups without a gate would only burn cycles on zeros.
+                {
+                    constexpr int TMv = NP == 1 ? 0 : 2;
+                    const unsigned long long sms = (unsigned long long)ctx->sm_count;
+                    if (A.count <= sms) return launch_br_g<L, BGBIT, NP, 1, 6, MODE, TMv>(ctx, A, s);
+                    if (A.count <= 2 * sms) return launch_br_g<L, BGBIT, NP, 2, 6, MODE, TMv>(ctx, A, s);
+                    return launch_br_g<L, BGBIT, NP, 4, 6, MODE, TMv>(ctx, A, s);
+                }
         }
     }
 }
@@ -276,6 +285,7 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
     c->P = P; c->device = device_id; c->flags = flags;
     c->NP = (flags & TFHE_B200_FLAG_UNSPLIT_FFT) ? 1 : 2;
     c->G = env_int("TFHE_B200_G", 0);
+    { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) c->sm_count = prop.multiProcessorCount; }
     c->chunk = (size_t)env_int("TFHE_B200_CHUNK", 1 << 16);
     ctx = c;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
