@@ -262,6 +262,14 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
+        traffic, traffic_src = None, "no ncu capture committed for this launch size (profiles/traffic.json)"
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            ent = tj["unsplit" if args.unsplit else "split"].get(str(B))
+            if ent:
+                traffic, traffic_src = ent["dram_bytes"], ent["source"]
+        except (OSError, KeyError, ValueError):
+            pass
         hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
         ks_gbs = Q_KSK_BYTES_PER_GATE * B / (ks_ms * 1e-3) / 1e9
         line = {
@@ -277,8 +285,8 @@ def main():
             "gpu_launches": int(launches),
             "single_bootstrap_latency_ms": lat,
             "roofline": {"bound": "fp64", "kernel": "blind_rotate_kernel", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak, "traffic": None,
-                         "traffic_note": "ncu --set full on a 4096-gate launch: dram read 304 MB + write 20 MB (profiles/r1/ncu_v5_blind_rotate_split.txt); keys are L2-resident, the kernel is not DRAM-bound",
+                         "frac": achieved / fp64_peak, "traffic": traffic,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one blind_rotate_kernel launch of this size (bytes); " + traffic_src + "; keys are L2-resident, the kernel is not DRAM-bound",
                          "peak_source": "FP64 FMA rate measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry); not tensor- or HBM-bound: keys are L2-resident",
                          "kernel_ms": br_ms, "algorithmic_flop_per_gate": W_FFT_FLOP_PER_GATE, "share_of_step": br_ms / (ms_total / args.steps)},
             "roofline_keyswitch": {"bound": "hbm", "kernel": "keyswitch_kernel", "achieved": ks_gbs, "peak": hbm_peak, "unit": "GB/s",
@@ -288,13 +296,15 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             octx = O.Context(keys)
-            sample = max(64, 8 * cores)
-            octx.gate(O.NAND, x[:cores], y[:cores], nthreads=cores)
+            t0 = time.perf_counter()
+            octx.gate(O.NAND, x[:cores], y[:cores], nthreads=cores)          # warm-up + rate estimate
+            rate = cores / (time.perf_counter() - t0)
+            sample = int(min(B, max(4 * cores, rate * 12.0)) // cores * cores) or cores   # ~12 s of CPU work
             t0 = time.perf_counter()
             ref = octx.gate(O.NAND, x[:sample], y[:sample], nthreads=cores)
             dt = time.perf_counter() - t0
             assert np.array_equal(ref, got[:sample]), "GPU ciphertexts differ from the oracle"
-            line["cpu_baseline"] = {"value": sample / dt, "unit": "gates/s", "cores": cores, "kind": "port",
+            line["cpu_baseline"] = {"value": sample / dt, "unit": "gates/s", "cores": cores, "kind": "port", "seconds": dt,
                                     "sample": f"first {sample} gates of the step's batch, one gate per OpenMP thread; GPU outputs bit-identical on this sample"}
         print(json.dumps(line))
     if world > 1:

@@ -46,3 +46,21 @@ def test_ripple_carry_adder_32bit(keypair):
         carry = T.gate_mux(ck, axb, carry, A[i])
         out |= T.decrypt(sk, s).astype(np.uint64) << np.uint64(i)
     assert np.array_equal(out, (xs + ys) & np.uint64(0xFFFFFFFF))
+
+
+def test_tutorial_circuit_device_resident(keypair):
+    """The same minimum circuit with every intermediate ciphertext kept in HBM (DeviceLweBatch): only the inputs
+    go up and only the 16 result bits come back.  Must agree bit for bit with the host-driven run."""
+    from tfhe_jl_b200 import _cabi
+    rng, sk, ck = keypair
+    ha, hb = T.encrypt(rng, sk, bits_of(2017, 16)), T.encrypt(rng, sk, bits_of(42, 16))
+    a, b = T.DeviceLweBatch.from_host(ha), T.DeviceLweBatch.from_host(hb)
+    carry = T.constant_dev(ck, False)
+    hcarry = T.gate_constant(ck, False)
+    for i in range(16):
+        carry = T.gate_dev(ck, _cabi.MUX, T.gate_dev(ck, _cabi.XNOR, a[i], b[i]), carry, a[i])
+        if i < 2:   # spot-check against the host-driven path
+            hcarry = T.gate_mux(ck, T.gate_xnor(ck, ha[i], hb[i]), hcarry, ha[i])
+            assert np.array_equal(carry.to_host().data[0], hcarry.data)
+    res = T.gate_dev(ck, _cabi.MUX, carry.repeat(16), b, a).to_host()
+    assert sum(int(v) << i for i, v in enumerate(T.decrypt(sk, res))) == 42

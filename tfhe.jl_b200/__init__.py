@@ -9,7 +9,7 @@ Only what the hot path needs lives here: ``csrc/`` (sm_100a kern
 """
 from . import _cabi
 from ._cabi import Context, TFHEB200Error, build, device_count, lib
-from .api import (CloudKey, CloudKeyPart, LweSample, MKCloudKey, MKLweSample, SchemeParameters, SecretKey,
+from .api import (CloudKey, CloudKeyPart, DeviceLweBatch, LweSample, constant_dev, gate_dev, MKCloudKey, MKLweSample, SchemeParameters, SecretKey,
                   SharedKey, decrypt, encrypt, gate_and, gate_andny, gate_andyn, gate_constant, gate_mux,
                   gate_nand, gate_nor, gate_not, gate_or, gate_orny, gate_oryn, gate_xnor, gate_xor,
                   make_key_pair, mk_decrypt, mk_encrypt, mk_gate_nand, mktfhe_parameters_2party,

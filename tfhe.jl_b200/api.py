@@ -388,3 +388,50 @@ def mk_gate_nand(ck: MKCloudKey, x: MKLweSample, y: MKLweSample) -> MKLweSample:
     single = x.data.ndim == 1
     out = ck.ctx.mk_nand(np.atleast_2d(x.data), np.atleast_2d(y.data))
     return MKLweSample(out[0] if single else out, ck.parties, 0.0)
+
+
+# ------------------------------------------------------------------ device-resident batches (levelised circuits)
+class DeviceLweBatch:
+    """A batch of LWE ciphertexts that STAYS in HBM between gates: dependent circuits such as
+    examples/tutorial.jl or a ripple-carry adder run level by level without a host round trip per gate.
+    `tensor` is a CUDA int32 torch tensor of shape [count][n+1] (PyTorch is only the device-memory plumbing)."""
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+
+    @classmethod
+    def from_host(cls, sample: LweSample):
+        import torch
+        return cls(torch.from_numpy(np.ascontiguousarray(np.atleast_2d(sample.data))).cuda())
+
+    def to_host(self) -> LweSample:
+        return LweSample(self.tensor.cpu().numpy(), 0.0)
+
+    def __len__(self):
+        return self.tensor.shape[0]
+
+    def __getitem__(self, idx):
+        t = self.tensor[idx]
+        return DeviceLweBatch(t if t.dim() == 2 else t[None, :])
+
+    def repeat(self, count: int):
+        return DeviceLweBatch(self.tensor.repeat(count, 1).contiguous())
+
+
+def gate_dev(ck: CloudKey, op: int, *xs: DeviceLweBatch) -> DeviceLweBatch:
+    """Any gate of gates.jl on device-resident operands: one asynchronous C-ABI call on torch's current stream."""
+    import torch
+    ts = [x.tensor.contiguous() for x in xs]
+    out = torch.empty_like(ts[0])
+    ptrs = [t.data_ptr() for t in ts] + [0] * (3 - len(ts))
+    ck.ctx.gate_dev(op, ptrs[0], ptrs[1], ptrs[2], out.data_ptr(), ts[0].shape[0], stream=torch.cuda.current_stream().cuda_stream)
+    return DeviceLweBatch(out)
+
+
+def constant_dev(ck: CloudKey, values) -> DeviceLweBatch:
+    """gate_constant (gates.jl:91-93) producing a device-resident batch."""
+    import torch
+    v = np.atleast_1d(np.asarray(values, dtype=bool))
+    flags = torch.zeros((v.size, ck.params.lwe_size + 1), dtype=torch.int32)
+    flags[:, 0] = torch.from_numpy(v.astype(np.int32))
+    return gate_dev(ck, _cabi.CONSTANT, DeviceLweBatch(flags.cuda()))

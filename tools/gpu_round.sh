@@ -7,8 +7,11 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smok
 timeout 600 python bench.py > gpurun_out/bench_split.json 2> gpurun_out/bench_split.err
 timeout 600 python bench.py --unsplit --no-cpu-baseline > gpurun_out/bench_unsplit.json 2> gpurun_out/bench_unsplit.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
-CMD="python bench.py --steps 2 --warmup 1 --batch 4096 --no-cpu-baseline"
-$CMD > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"   # the default workload (2^16 gates per launch)
+$CMD > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 $CMD > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:blind_rotate -s 1 -c 1 -f -o gpurun_out/prof_blind_rotate $CMD > gpurun_out/ncu_full.log 2>&1
 $CMD > gpurun_out/plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:keyswitch -s 1 -c 1 -f -o gpurun_out/prof_keyswitch $CMD > gpurun_out/ncu_full_ks.log 2>&1
+timeout 300 python tools/circuit_latency.py > gpurun_out/circuits_split.json 2> gpurun_out/circuits.err
+FLAGS=1 CPU=0 timeout 300 python tools/circuit_latency.py > gpurun_out/circuits_unsplit.json 2>> gpurun_out/circuits.err
+cat gpurun_out/circuits_split.json gpurun_out/circuits_unsplit.json
 tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/smoke.log; cat gpurun_out/bench_split.json gpurun_out/bench_unsplit.json gpurun_out/bench_reference.json | cut -c1-1800; tail -2 gpurun_out/bench_split.err
