@@ -81,3 +81,20 @@ def test_mk_api_mirror_2party():
     assert np.array_equal(T.mk_decrypt(sks, e1), m1)
     out = T.mk_gate_nand(ck, e1, e2)
     assert np.array_equal(T.mk_decrypt(sks, out), ~(m1 & m2))
+
+
+@pytest.mark.parametrize("p,count", [(2, 601), (4, 310), (8, 9)])
+def test_mk_nand_large_batch_ring_configurations(p, count, monkeypatch):
+    """Batches above 2 x SM count take the 4-gates-per-CTA ring kernel (6-stage ring for 2 parties, 3-stage
+    for 4); ragged counts leave groups without a gate in the last CTA.  Every ciphertext must equal the
+    oracle's, and the one-gate-per-CTA kernel (TFHE_B200_MK_RING=0) must agree too."""
+    mk = O.mk_keygen(O.small_params(O.MK_PARAMS[p], 3), p, 70 + p)
+    octx = O.MKContext(mk)
+    bits = np.random.default_rng(p).integers(0, 2, (count, 2)).astype(bool)
+    rng = O.Rng(p)
+    x, y = O.mk_encrypt(rng, mk, bits[:, 0]), O.mk_encrypt(rng, mk, bits[:, 1])
+    want = octx.nand(x, y)
+    assert np.array_equal(make_mk_ctx(mk).mk_nand(x, y), want)
+    assert np.array_equal(make_mk_ctx(mk, _cabi.FLAG_UNSPLIT_FFT).mk_nand(x, y), want)
+    monkeypatch.setenv("TFHE_B200_MK_RING", "0")
+    assert np.array_equal(make_mk_ctx(mk).mk_nand(x, y), want)

@@ -17,6 +17,7 @@
 #include "kernels.cuh"
 #include "blind_rotate.cuh"
 #include "mk_kernels.cuh"
+#include "mk_blind_rotate.cuh"
 
 using namespace tfhe_b200;
 
@@ -38,6 +39,7 @@ struct tfhe_b200_ctx {
     int NP = 2;
     int G = 0;                       // gates per CTA of the blind-rotation kernel (0 = default, see launch_br_np)
     int sm_count = 148;
+    int mk_ring = 1;                 // MK blind rotation: 1 = TMA key ring, several gates per CTA (mk_blind_rotate.cuh)
     cudaStream_t stream = nullptr;   // used by the host-buffer entry points
     double2* d_E = nullptr;          // exp(-i*pi*x/1024), x < 2048
     double2* d_bk_fft = nullptr;     // single-key: [n][l][2][2][NP][512]; MK: [p][n][l*(2p+2)][NP][512]
@@ -45,6 +47,11 @@ struct tfhe_b200_ctx {
     int ksk_stride = 0;
     bool have_bk = false, have_ksk = false;
     DevBuf bx, by, bz, bout, bu1, bu2, bidx, bidx2;
+    // The scratch buffers above are shared by every entry point.  Calls are stream-ordered on the stream they are
+    // given, so a call on a DIFFERENT stream than the previous user first waits for that user's event.
+    cudaEvent_t scratch_ev = nullptr;
+    cudaStream_t scratch_stream = nullptr;
+    bool scratch_busy = false;
     std::mutex mu;
     std::string err;
     std::atomic<uint64_t> launches{0};
@@ -64,6 +71,16 @@ int fail(tfhe_b200_ctx* c, int code, const std::string& msg) {
         if (e_ != cudaSuccess)                                                                           \
             return fail(ctx, TFHE_B200_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
     } while (0)
+
+struct ScratchGuard {
+    tfhe_b200_ctx* c; cudaStream_t s;
+    ScratchGuard(tfhe_b200_ctx* ctx, cudaStream_t stream) : c(ctx), s(stream) {
+        if (c->scratch_busy && c->scratch_stream != s) cudaStreamWaitEvent(s, c->scratch_ev, 0);
+    }
+    ~ScratchGuard() {
+        if (cudaEventRecord(c->scratch_ev, s) == cudaSuccess) { c->scratch_stream = s; c->scratch_busy = true; }
+    }
+};
 
 int reserve(tfhe_b200_ctx* ctx, DevBuf& b, size_t bytes) {
     if (b.cap >= bytes) return 0;
@@ -285,10 +302,12 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
     c->P = P; c->device = device_id; c->flags = flags;
     c->NP = (flags & TFHE_B200_FLAG_UNSPLIT_FFT) ? 1 : 2;
     c->G = env_int("TFHE_B200_G", 0);
+    c->mk_ring = env_int("TFHE_B200_MK_RING", 1);
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) c->sm_count = prop.multiProcessorCount; }
     c->chunk = (size_t)env_int("TFHE_B200_CHUNK", 1 << 16);
     ctx = c;
-    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    cudaError_t e = cudaEventCreateWithFlags(&c->scratch_ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return fail(nullptr, TFHE_B200_ECUDA, cudaGetErrorString(e)); }
     // twiddle table E[x] = exp(-i*pi*x/1024), computed in long double
     std::vector<double2> E(2048);
@@ -307,6 +326,7 @@ void tfhe_b200_destroy(tfhe_b200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->scratch_ev) cudaEventDestroy(c->scratch_ev);
     for (DevBuf* b : {&c->bx, &c->by, &c->bz, &c->bout, &c->bu1, &c->bu2, &c->bidx, &c->bidx2})
         if (b->p) cudaFree(b->p);
     if (c->d_E) cudaFree(c->d_E);
@@ -391,6 +411,7 @@ int tfhe_b200_gate_batch_dev(tfhe_b200_ctx* ctx, int op, const int32_t* x, const
     const size_t wu = (size_t)ctx->P.N * ctx->P.k + 1;
     if ((rc = reserve(ctx, ctx->bu1, count * wu * 4))) return rc;
     if (op == TFHE_B200_MUX && (rc = reserve(ctx, ctx->bu2, count * wu * 4))) return rc;
+    ScratchGuard guard(ctx, (cudaStream_t)stream);
     return gate_dev(ctx, op, x, y, z, out, count, (int32_t*)ctx->bu1.p, (int32_t*)ctx->bu2.p, (cudaStream_t)stream);
 }
 
@@ -415,6 +436,7 @@ template <typename F>
 static int host_chunks(tfhe_b200_ctx* ctx, const int32_t* const hin[3], const size_t win[3], int32_t* hout, size_t wout,
                        size_t count, F&& body) {
     DevBuf* bin[3] = {&ctx->bx, &ctx->by, &ctx->bz};
+    ScratchGuard guard(ctx, ctx->stream);
     for (size_t off = 0; off < count; off += ctx->chunk) {
         size_t cnt = std::min(ctx->chunk, count - off);
         int rc;
