@@ -238,3 +238,34 @@ def test_api_mirror_truth_tables():
     octx = O.Context(O.KeySet(O.PARAMS_80, sk.key, None, ck.bootstrap_key, ck.keyswitch_key))
     x, y = T.encrypt(rng, sk, tt[:, 0]), T.encrypt(rng, sk, tt[:, 1])
     assert np.array_equal(T.gate_and(ck, x, y).data, octx.gate(O.AND, x.data, y.data))
+
+
+@pytest.mark.parametrize("flags", [_cabi.FLAG_SPLIT_FFT, _cabi.FLAG_UNSPLIT_FFT], ids=["split", "unsplit"])
+@pytest.mark.parametrize("count", [3, 148, 149, 444, 445, 601])
+def test_every_batch_size_dispatch_path_equals_oracle(keys80_small, octx80_small, flags, count):
+    """The library picks a kernel shape by batch size: up to 3 gates per SM the latency kernel (one gate per CTA
+    spread over 4 groups, 1-3 waves) + sliced key switch, above that four gates per CTA.  With a short LWE key
+    (n = 24) the oracle can check EVERY ciphertext of every path; 445 / 601 leave the last CTA ragged."""
+    P = keys80_small.params
+    ctx = T.Context(n=P.n, l=P.l, bgbit=P.bgbit, t=P.t, basebit=P.basebit, flags=flags)
+    ctx.load_bk(keys80_small.bk); ctx.load_ksk(keys80_small.ksk)
+    bits = np.random.default_rng(count).integers(0, 2, (count, 3)).astype(bool)
+    rng = O.Rng(count)
+    x, y, z = (O.encrypt(rng, keys80_small, bits[:, i]) for i in range(3))
+    assert np.array_equal(ctx.gate(O.NAND, x, y), octx80_small.gate(O.NAND, x, y))
+    assert np.array_equal(ctx.gate(O.MUX, x, y, z), octx80_small.gate(O.MUX, x, y, z))
+
+
+def test_latency_path_can_be_disabled_and_agrees(keys80, gctx80, monkeypatch):
+    """TFHE_B200_LOWLAT=0 routes small batches through the throughput kernels (1 and 2 gates per CTA) and the
+    one-CTA-per-ciphertext key switch; same ciphertexts."""
+    rng = O.Rng(21)
+    bits = np.random.default_rng(21).integers(0, 2, (150, 2)).astype(bool)
+    x, y = O.encrypt(rng, keys80, bits[:, 0]), O.encrypt(rng, keys80, bits[:, 1])
+    want = gctx80.gate(O.XOR, x, y)
+    monkeypatch.setenv("TFHE_B200_LOWLAT", "0")
+    P = keys80.params
+    ctx = T.Context(n=P.n, l=P.l, bgbit=P.bgbit, t=P.t, basebit=P.basebit)
+    ctx.load_bk(keys80.bk); ctx.load_ksk(keys80.ksk)
+    assert np.array_equal(ctx.gate(O.XOR, x, y), want)            # 150 gates: 2 per CTA
+    assert np.array_equal(ctx.gate(O.XOR, x[:3], y[:3]), want[:3])  # 3 gates: 1 per CTA

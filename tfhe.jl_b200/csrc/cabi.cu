@@ -16,6 +16,7 @@
 
 #include "kernels.cuh"
 #include "blind_rotate.cuh"
+#include "blind_rotate_lowlat.cuh"
 #include "mk_kernels.cuh"
 #include "mk_blind_rotate.cuh"
 
@@ -39,6 +40,7 @@ struct tfhe_b200_ctx {
     int NP = 2;
     int G = 0;                       // gates per CTA of the blind-rotation kernel (0 = default, see launch_br_np)
     int sm_count = 148;
+    int lowlat = 1;                  // batches of <= 1 gate per SM: one gate per CTA spread over 4 groups + sliced key switch
     int mk_ring = 1;                 // MK blind rotation: 1 = TMA key ring, several gates per CTA (mk_blind_rotate.cuh)
     cudaStream_t stream = nullptr;   // used by the host-buffer entry points
     double2* d_E = nullptr;          // exp(-i*pi*x/1024), x < 2048
@@ -137,6 +139,18 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
                 {
                     constexpr int TMv = NP == 1 ? 0 : 2;
                     const unsigned long long sms = (unsigned long long)ctx->sm_count;
+                    // measured (tools/latency_probe.py): one wave of 148 gates takes 1.95 ms on the latency kernel,
+                    // 592 gates 6.45 ms on the 4-gates-per-CTA kernel, so up to 3 waves the latency kernel also wins
+                    if (A.count <= 3 * sms && ctx->lowlat && br_lowlat_smem_bytes<L, NP>(A.n_pad) <= 227 * 1024) {
+                        // latency path (blind_rotate_lowlat.cuh): one gate per CTA, one digit polynomial per group
+                        auto kern = blind_rotate_lowlat_kernel<L, BGBIT, NP>;
+                        const size_t smem = br_lowlat_smem_bytes<L, NP>(A.n_pad);
+                        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        kern<<<(unsigned)A.count, 64 * 2 * L, smem, s>>>(A);
+                        CU(cudaGetLastError());
+                        ctx->launches++;
+                        return 0;
+                    }
                     if (A.count <= sms) return launch_br_g<L, BGBIT, NP, 1, 6, MODE, TMv>(ctx, A, s);
                     if (A.count <= 2 * sms) return launch_br_g<L, BGBIT, NP, 2, 6, MODE, TMv>(ctx, A, s);
                     return launch_br_g<L, BGBIT, NP, 4, 6, MODE, TMv>(ctx, A, s);
@@ -185,6 +199,15 @@ int launch_keyswitch(tfhe_b200_ctx* ctx, const int32_t* in, int32_t* out, size_t
     A.n = P.n; A.Nk = P.N * P.k; A.t = P.t; A.basebit = P.basebit; A.stride = ctx->ksk_stride;
     A.in_stride = A.Nk + 1; A.in_offset = 0; A.in_b_offset = A.Nk;
     A.out_stride = P.n + 1; A.out_offset = 0; A.b_offset = P.n; A.b_mode = 0;
+    if (count <= 3 * (size_t)ctx->sm_count && ctx->lowlat) {
+        // latency path: several CTAs per ciphertext (keyswitch_sliced_kernel)
+        const int slices = (int)std::min<size_t>(32, std::max<size_t>(1, (size_t)16 * ctx->sm_count / count));
+        CU(cudaMemsetAsync(out, 0, count * (size_t)(P.n + 1) * sizeof(int32_t), s));
+        keyswitch_sliced_kernel<<<(unsigned)(count * slices), A.stride / 4, (size_t)(A.Nk / slices + 1) * sizeof(int32_t), s>>>(A, count, slices);
+        CU(cudaGetLastError());
+        ctx->launches++;
+        return 0;
+    }
     return launch_keyswitch_args(ctx, A, count, s);
 }
 
@@ -303,6 +326,7 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
     c->NP = (flags & TFHE_B200_FLAG_UNSPLIT_FFT) ? 1 : 2;
     c->G = env_int("TFHE_B200_G", 0);
     c->mk_ring = env_int("TFHE_B200_MK_RING", 1);
+    c->lowlat = env_int("TFHE_B200_LOWLAT", 1);
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) c->sm_count = prop.multiProcessorCount; }
     c->chunk = (size_t)env_int("TFHE_B200_CHUNK", 1 << 16);
     ctx = c;

@@ -318,6 +318,53 @@ __global__ void keyswitch_kernel(KeyswitchArgs A, unsigned long long count) {
     }
 }
 
+// Small batches (dependent circuits): one CTA per ciphertext would leave most SMs idle and make the key switch
+// a 1 024-step chain of L2 round trips.  Here `slices` CTAs share a ciphertext: each gathers a contiguous range of
+// mask positions and adds its partial sums into `out` — zero-initialised by the caller — with integer atomics
+// (integer addition commutes, so the result is the same bits as keyswitch_kernel); slice 0 also adds the input b.
+// Single-key layout only (b_mode 0).
+__global__ void keyswitch_sliced_kernel(KeyswitchArgs A, unsigned long long count, int slices) {
+    extern __shared__ int32_t s_a[];
+    const size_t g = blockIdx.x / slices;
+    const int sl = blockIdx.x % slices;
+    if (g >= count) return;
+    const int i0 = (int)((long long)A.Nk * sl / slices), i1 = (int)((long long)A.Nk * (sl + 1) / slices);
+    const int32_t* in = A.in + g * A.in_stride + A.in_offset;
+    const uint32_t prec = 1u << (32 - (1 + A.basebit * A.t));   // keyswitch.jl:58
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) s_a[i - i0] = (int32_t)((uint32_t)in[i] + prec);
+    __syncthreads();
+    const int base1 = (1 << A.basebit) - 1;
+    const uint32_t mask = (uint32_t)base1;
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    const uint4* rows = reinterpret_cast<const uint4*>(A.ksk) + threadIdx.x;
+    const size_t row_q = (size_t)A.stride / 4;
+    for (int i = i0; i < i1; i++) {
+        const uint32_t ai = (uint32_t)s_a[i - i0];
+        const uint4* ri = rows + (size_t)i * A.t * base1 * row_q;
+#pragma unroll 8
+        for (int j = 0; j < A.t; j++) {
+            uint32_t d = (ai >> (32 - (j + 1) * A.basebit)) & mask;   // keyswitch.jl:63-67
+            if (d) {
+                uint4 v = __ldg(ri + ((size_t)j * base1 + (d - 1)) * row_q);
+                acc.x -= v.x; acc.y -= v.y; acc.z -= v.z; acc.w -= v.w;   // keyswitch.jl:71-77
+            }
+        }
+    }
+    const int c0 = threadIdx.x * 4;
+    unsigned int* o = reinterpret_cast<unsigned int*>(A.out + g * A.out_stride + A.out_offset);
+    uint32_t vals[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        int c = c0 + e;
+        if (c < A.n) atomicAdd(o + c, vals[e]);
+        else if (c == A.n) {
+            uint32_t v = vals[e];
+            if (sl == 0) v += (uint32_t)A.in[g * A.in_stride + A.in_b_offset];
+            atomicAdd(reinterpret_cast<unsigned int*>(A.out_b + g * A.out_stride + A.b_offset), v);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Row-wise linear combination of ciphertext batches: out = ka*x + kb*y + (0,...,0,cb)
 // (gate_not gates.jl:76-79, gate_constant :91-93, the OR step of gate_mux :174, MK prologue mk_gates.jl:8-10)
