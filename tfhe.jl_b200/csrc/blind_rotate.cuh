@@ -217,6 +217,11 @@ struct BlindRotateArgs {
     // MODE 0 (bootstrap_wo_keyswitch with fused gate prologue): lin = ka*x + kb*y + (0, cb)
     const int32_t* x; const int32_t* y;
     int32_t ka, kb, cb, mu;
+    // gate_mux (gates.jl:163-171) runs its two bootstraps in one launch: gates g >= half take their inputs from
+    // (x2, y2)[g - half] and the second set of prologue constants (half == 0: unused)
+    const int32_t* x2; const int32_t* y2;
+    int32_t ka2, kb2, cb2;
+    unsigned long long half;
     // MODE 1 (raw blind_rotate on given accumulators)
     const int32_t* acc_in; const int32_t* bara_in;
     int32_t* out;            // MODE 0: [count][N+1] extracted LWE; MODE 1: [count][2][N]
@@ -283,15 +288,19 @@ __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs
         for (int i = t; i < A.n_iter; i += 64) bara[i] = 0;
     } else if (MODE == 0) {
         // gate prologue (gates.jl) + modulus switch (bootstrap.jl:74-75)
-        const int32_t* xr = A.x + g * (A.n + 1);
-        const int32_t* yr = A.y ? A.y + g * (A.n + 1) : nullptr;
+        const bool second = A.half != 0 && g >= A.half;
+        const unsigned long long gi = second ? g - A.half : g;
+        const int32_t* xr = (second ? A.x2 : A.x) + gi * (A.n + 1);
+        const int32_t* yb = second ? A.y2 : A.y;
+        const int32_t* yr = yb ? yb + gi * (A.n + 1) : nullptr;
+        const int32_t ka = second ? A.ka2 : A.ka, kb = second ? A.kb2 : A.kb, cb = second ? A.cb2 : A.cb;
         for (int i = t; i < A.n; i += 64) {
-            uint32_t v = (uint32_t)A.ka * (uint32_t)xr[i];
-            if (yr) v += (uint32_t)A.kb * (uint32_t)yr[i];
+            uint32_t v = (uint32_t)ka * (uint32_t)xr[i];
+            if (yr) v += (uint32_t)kb * (uint32_t)yr[i];
             bara[i] = modswitch2048((int32_t)v);
         }
-        uint32_t vb = (uint32_t)A.ka * (uint32_t)xr[A.n] + (uint32_t)A.cb;
-        if (yr) vb += (uint32_t)A.kb * (uint32_t)yr[A.n];
+        uint32_t vb = (uint32_t)ka * (uint32_t)xr[A.n] + (uint32_t)cb;
+        if (yr) vb += (uint32_t)kb * (uint32_t)yr[A.n];
         const int barb = modswitch2048((int32_t)vb);
         // acc = (0, X^{-barb} * (mu, ..., mu))   (bootstrap.jl:54-56,78)
         const int s = (-barb) & 2047;

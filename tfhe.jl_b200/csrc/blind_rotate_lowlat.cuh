@@ -15,7 +15,7 @@
 //
 // so the critical path of an iteration is one forward transform, 4 spectrum MACs and one inverse transform
 // instead of 4 + 16 + 4.  Results are bit-identical to K3 (same transforms, the sums over q are taken in the
-// same order).  Used for batches of at most one gate per SM.
+// same order).  Used for batches of up to three gates per SM (cabi.cu, launch_br_np).
 #pragma once
 #include "blind_rotate.cuh"
 
@@ -66,15 +66,19 @@ __global__ void __launch_bounds__(64 * 2 * L, 1) blind_rotate_lowlat_kernel(Blin
 
     // gate prologue (gates.jl) + modulus switch (bootstrap.jl:74-75), all threads of the CTA
     {
-        const int32_t* xr = A.x + g * (A.n + 1);
-        const int32_t* yr = A.y ? A.y + g * (A.n + 1) : nullptr;
+        const bool second = A.half != 0 && g >= A.half;   // second bootstrap of gate_mux
+        const unsigned long long gi = second ? g - A.half : g;
+        const int32_t* xr = (second ? A.x2 : A.x) + gi * (A.n + 1);
+        const int32_t* yb = second ? A.y2 : A.y;
+        const int32_t* yr = yb ? yb + gi * (A.n + 1) : nullptr;
+        const int32_t ka = second ? A.ka2 : A.ka, kb = second ? A.kb2 : A.kb, cb = second ? A.cb2 : A.cb;
         for (int i = threadIdx.x; i < A.n; i += blockDim.x) {
-            uint32_t v = (uint32_t)A.ka * (uint32_t)xr[i];
-            if (yr) v += (uint32_t)A.kb * (uint32_t)yr[i];
+            uint32_t v = (uint32_t)ka * (uint32_t)xr[i];
+            if (yr) v += (uint32_t)kb * (uint32_t)yr[i];
             bara[i] = modswitch2048((int32_t)v);
         }
-        uint32_t vb = (uint32_t)A.ka * (uint32_t)xr[A.n] + (uint32_t)A.cb;
-        if (yr) vb += (uint32_t)A.kb * (uint32_t)yr[A.n];
+        uint32_t vb = (uint32_t)ka * (uint32_t)xr[A.n] + (uint32_t)cb;
+        if (yr) vb += (uint32_t)kb * (uint32_t)yr[A.n];
         const int barb = modswitch2048((int32_t)vb);
         const int s0 = (-barb) & 2047;   // acc = (0, X^{-barb} * (mu, ..., mu))   (bootstrap.jl:54-56,78)
         for (int x = threadIdx.x; x < kN; x += blockDim.x) {

@@ -287,9 +287,15 @@ int gate_dev(tfhe_b200_ctx* ctx, int op, const int32_t* x, const int32_t* y, con
             return launch_lincomb(ctx, x, nullptr, out, 0, 0, kMu8, w, count, 1, s);
         case TFHE_B200_MUX:
             if (!x || !y || !z) return fail(ctx, TFHE_B200_EINVAL, "MUX needs x, y and z");
-            if ((rc = bootstrap_wo_ks_dev(ctx, x, y, 1, 1, -kMu8, kMu8, u1, count, s))) return rc;    // gates.jl:166-167
-            if ((rc = bootstrap_wo_ks_dev(ctx, x, z, -1, 1, -kMu8, kMu8, u2, count, s))) return rc;   // gates.jl:170-171
-            if ((rc = launch_lincomb(ctx, u1, u2, u1, 1, 1, kMu8, wu, count, 0, s))) return rc;       // gates.jl:174
+            {   // both bootstraps in ONE launch of 2*count gates: u1 = [AND(x, y) rows | AND(NOT x, z) rows]
+                BlindRotateArgs A = br_args(ctx, 2 * count);
+                A.x = x; A.y = y; A.ka = 1; A.kb = 1; A.cb = -kMu8;                                   // gates.jl:166-167
+                A.x2 = x; A.y2 = z; A.ka2 = -1; A.kb2 = 1; A.cb2 = -kMu8; A.half = count;             // gates.jl:170-171
+                A.mu = kMu8; A.out = u1;
+                if ((rc = launch_br<0>(ctx, A, s))) return rc;
+            }
+            (void)u2;
+            if ((rc = launch_lincomb(ctx, u1, u1 + count * (size_t)wu, u1, 1, 1, kMu8, wu, count, 0, s))) return rc;   // gates.jl:174
             return launch_keyswitch(ctx, u1, out, count, s);                                          // gates.jl:176
         default:
             return fail(ctx, TFHE_B200_EINVAL, "unknown gate opcode");
@@ -433,8 +439,7 @@ int tfhe_b200_gate_batch_dev(tfhe_b200_ctx* ctx, int op, const int32_t* x, const
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t wu = (size_t)ctx->P.N * ctx->P.k + 1;
-    if ((rc = reserve(ctx, ctx->bu1, count * wu * 4))) return rc;
-    if (op == TFHE_B200_MUX && (rc = reserve(ctx, ctx->bu2, count * wu * 4))) return rc;
+    if ((rc = reserve(ctx, ctx->bu1, (op == TFHE_B200_MUX ? 2 : 1) * count * wu * 4))) return rc;
     ScratchGuard guard(ctx, (cudaStream_t)stream);
     return gate_dev(ctx, op, x, y, z, out, count, (int32_t*)ctx->bu1.p, (int32_t*)ctx->bu2.p, (cudaStream_t)stream);
 }
@@ -490,8 +495,7 @@ int tfhe_b200_gate_batch(tfhe_b200_ctx* ctx, int op, const int32_t* x, const int
     const size_t win[3] = {w, w, w};
     return host_chunks(ctx, hin, win, out, w, count, [&](int32_t* dx, int32_t* dy, int32_t* dz, int32_t* dout, size_t cnt) {
         int r;
-        if ((r = reserve(ctx, ctx->bu1, cnt * wu * 4))) return r;
-        if (op == TFHE_B200_MUX && (r = reserve(ctx, ctx->bu2, cnt * wu * 4))) return r;
+        if ((r = reserve(ctx, ctx->bu1, (op == TFHE_B200_MUX ? 2 : 1) * cnt * wu * 4))) return r;
         return gate_dev(ctx, op, dx, dy, dz, dout, cnt, (int32_t*)ctx->bu1.p, (int32_t*)ctx->bu2.p, ctx->stream);
     });
 }

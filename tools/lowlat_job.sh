@@ -2,5 +2,4 @@
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
 timeout 300 python tools/latency_probe.py > gpurun_out/latency.json 2> gpurun_out/latency.err; cat gpurun_out/latency.json; tail -2 gpurun_out/latency.err
-TFHE_B200_LOWLAT=0 timeout 300 python tools/latency_probe.py
-CPU=0 timeout 300 python tools/circuit_latency.py; FLAGS=1 CPU=0 timeout 300 python tools/circuit_latency.py
+CPU=0 timeout 300 python tools/circuit_latency.py | tee gpurun_out/circuits_split.json; FLAGS=1 CPU=0 timeout 300 python tools/circuit_latency.py | tee gpurun_out/circuits_unsplit.json
