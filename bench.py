@@ -107,8 +107,29 @@ def run_reference(args, rank, world):
     with all host threads, on a bounded sample of the same workload per step."""
     if rank != 0:
         return
-    from oracle import oracle as O
     cores = os.cpu_count() or 1
+    # Genuine TFHE.jl when a Julia install and a TFHE.jl checkout are present (never the case in the build image
+    # or on the GPU boxes of this pool; kept so the arm upgrades itself from "port" to "reference").
+    import shutil
+    proj = os.environ.get("TFHE_JL_PROJECT", "")
+    if shutil.which("julia") and os.path.isdir(proj):
+        sample = max(32, 4 * cores)
+        r = subprocess.run(["julia", "--threads=auto", f"--project={proj}", os.path.join(ROOT, "tfhe.jl_b200", "julia", "cpu_baseline.jl"),
+                            str(sample), str(args.steps), str(args.warmup)], capture_output=True, text=True)
+        try:
+            j = json.loads(r.stdout.strip().splitlines()[-1])
+            desc = f"{sample} NAND gates per step through TFHE.jl gate_nand, {j['cores']} Julia thread(s)"
+            print(json.dumps({
+                "impl": "reference", "metric": METRIC, "value": j["gates_per_s"], "unit": "gates/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": j["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "batched NAND gate bootstrap, 80-bit params (n=500, N=1024, k=1, l=2, Bg=2^10)", "sample": desc},
+                "cpu_baseline": {"value": j["gates_per_s"], "unit": "gates/s", "cores": j["cores"], "kind": "reference", "sample": desc},
+                "e2e": {"value": j["gates_per_s"], "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+            return
+        except (IndexError, KeyError, ValueError):
+            pass   # fall through to the port
+    from oracle import oracle as O
     keys = O.keygen(O.PARAMS_80, 123)
     ctx = O.Context(keys)
     sample = max(32, 4 * cores)                       # gates per step: ~0.2 s per step on any core count

@@ -64,3 +64,28 @@ def test_tutorial_circuit_device_resident(keypair):
             assert np.array_equal(carry.to_host().data[0], hcarry.data)
     res = T.gate_dev(ck, _cabi.MUX, carry.repeat(16), b, a).to_host()
     assert sum(int(v) << i for i, v in enumerate(T.decrypt(sk, res))) == 42
+
+
+def test_levelised_minimum_circuit_equals_gate_by_gate(keypair):
+    """circuit.py batches all gates of a level into one launch; the ciphertexts must be the ones a gate-by-gate
+    evaluation (the reference's order) produces."""
+    from tfhe_jl_b200 import _cabi
+    from tfhe_jl_b200.circuit import minimum_circuit
+    rng, sk, ck = keypair
+    ha, hb = T.encrypt(rng, sk, bits_of(1234, 16)), T.encrypt(rng, sk, bits_of(4321, 16))
+    out = minimum_circuit(16).run(ck, {"a": ha, "b": hb})["min"].to_host()
+    assert sum(int(v) << i for i, v in enumerate(T.decrypt(sk, out))) == 1234
+    a, b = T.DeviceLweBatch.from_host(ha), T.DeviceLweBatch.from_host(hb)
+    lt = T.constant_dev(ck, False)
+    for i in range(16):
+        lt = T.gate_dev(ck, _cabi.MUX, T.gate_dev(ck, _cabi.XNOR, a[i], b[i]), lt, a[i])
+    want = T.gate_dev(ck, _cabi.MUX, lt.repeat(16), b, a).to_host()
+    assert np.array_equal(out.data, want.data)
+
+
+def test_levelised_adder32(keypair):
+    from tfhe_jl_b200.circuit import adder_circuit
+    rng, sk, ck = keypair
+    x, y = 0xDEADBEEF, 0x12345678
+    out = adder_circuit(32).run(ck, {"a": T.encrypt(rng, sk, bits_of(x, 32)), "b": T.encrypt(rng, sk, bits_of(y, 32))})
+    assert sum(int(v) << i for i, v in enumerate(T.decrypt(sk, out["sum"].to_host()))) == (x + y) & 0xFFFFFFFF

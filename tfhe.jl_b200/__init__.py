@@ -16,3 +16,5 @@ from .api import (CloudKey, CloudKeyPart, DeviceLweBatch, LweSample, constant_de
                   mktfhe_parameters_4party, mktfhe_parameters_8party, tfhe_parameters_80, tfhe_parameters_128)
 
 __all__ = [n for n in dir() if not n.startswith("_")]
+
+from .circuit import Circuit, Wire, adder_circuit, minimum_circuit  # noqa: E402,F401

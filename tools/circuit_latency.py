@@ -78,6 +78,18 @@ def main():
     res["adder32_ms"] = ms
     res["adder32_gate_depth"] = 1 + 31 * 2 + 1
 
+    # the same circuits through the levelised driver (tfhe.jl_b200/circuit.py): all ready gates of a level in one launch
+    from tfhe_jl_b200.circuit import adder_circuit, minimum_circuit
+    cm, ca = minimum_circuit(16), adder_circuit(32)
+    ia = {"a": T.DeviceLweBatch.from_host(T.encrypt(rng, sk, bits_of(2017, 16))), "b": T.DeviceLweBatch.from_host(T.encrypt(rng, sk, bits_of(42, 16)))}
+    out, ms = timed(lambda: cm.run(ck, ia)["min"])
+    assert value_of(T.decrypt(sk, out.to_host())) == 42
+    res["tutorial_min16_levelised_ms"], res["tutorial_levels"] = ms, cm.depth
+    ib = {"a": a, "b": b}
+    out, ms = timed(lambda: ca.run(ck, ib)["sum"])
+    assert value_of(T.decrypt(sk, out.to_host())) == (x + y) & 0xFFFFFFFF
+    res["adder32_levelised_ms"], res["adder32_levels"] = ms, ca.depth
+
     if os.environ.get("CPU", "1") == "1":
         from oracle import oracle as O
         keys = O.keygen(O.PARAMS_80, 5)
