@@ -41,6 +41,7 @@ def test_minimum_circuit_schedule():
     c = minimum_circuit(16)
     assert c.depth == 18                       # 1 (all XNORs at once) + 16 (MUX chain) + 1 (select)
     assert c.bootstraps == 80                  # 80 blind rotations in examples/tutorial.jl
+    assert c.launches == 18
     lv = c.levels()
     assert [op for op, _, _ in lv[1]] == [_cabi.XNOR] and lv[1][0][1].shape == (2, 16)
     rng = np.random.default_rng(0)
@@ -51,6 +52,7 @@ def test_minimum_circuit_schedule():
 def test_adder_circuit_schedule():
     c = adder_circuit(32)
     assert c.depth == 33
+    assert c.launches == 33                    # 1 (all propagate XORs) + 31 (carry MUX chain) + 1 (all sum XORs)
     rng = np.random.default_rng(1)
     for a, b in [(0xDEADBEEF, 0x12345678), (0xFFFFFFFF, 1), (0, 0)] + [tuple(rng.integers(0, 2 ** 32, 2)) for _ in range(20)]:
         got = value(run_plain(c, {"a": bits(int(a), 32), "b": bits(int(b), 32)})["sum"])
@@ -77,3 +79,36 @@ def test_arity_is_checked():
         c.gate(_cabi.NAND, a)
     with pytest.raises(ValueError):
         c.gate(_cabi.CONSTANT)
+
+
+def test_random_dags_schedule_is_valid_and_equivalent():
+    """Random circuits with every gate type: the slack-aware schedule never reads a wire before it is produced
+    (asserted inside run_plain) and computes what gate-by-gate evaluation in creation order computes."""
+    rng = np.random.default_rng(7)
+    binary = [_cabi.NAND, _cabi.OR, _cabi.AND, _cabi.XOR, _cabi.XNOR, _cabi.NOR]
+    for trial in range(30):
+        c = Circuit()
+        wires = c.input("x", 6) + [c.constant(bool(trial & 1))]
+        ref = {}                                   # wire index -> function of the input bits (evaluated eagerly below)
+        xin = rng.integers(0, 2, 6).astype(bool)
+        val = {w.index: bool(v) for w, v in zip(wires[:6], xin)}
+        val[wires[6].index] = bool(trial & 1)
+        for _ in range(40):
+            kind = rng.integers(0, 10)
+            if kind == 0:
+                a = wires[rng.integers(len(wires))]
+                w = c.not_(a); val[w.index] = not val[a.index]
+            elif kind == 1:
+                a, b, d = (wires[i] for i in rng.integers(0, len(wires), 3))
+                w = c.mux(a, b, d); val[w.index] = val[b.index] if val[a.index] else val[d.index]
+            else:
+                op = binary[rng.integers(len(binary))]
+                a, b = (wires[i] for i in rng.integers(0, len(wires), 2))
+                w = c.gate(op, a, b)
+                val[w.index] = bool(PLAIN[op](np.array(val[a.index]), np.array(val[b.index])))
+            wires.append(w)
+        outs = [wires[i] for i in rng.integers(6, len(wires), 8)]
+        c.output("o", outs)
+        got = run_plain(c, {"x": xin})["o"]
+        assert list(got) == [val[w.index] for w in outs], trial
+        assert c.launches <= sum(1 for op, _, _ in c._gates if op not in (_cabi.NOT, _cabi.CONSTANT))

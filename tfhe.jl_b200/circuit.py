@@ -85,8 +85,52 @@ class Circuit:
         return max(self._level, default=0)
 
     @property
+    def launches(self) -> int:
+        """Bootstrapped (level, opcode) batches = sequential bootstrap latencies of one run."""
+        return sum(1 for steps in self.levels() for op, _, _ in steps if op not in _FREE)
+
+    @property
     def bootstraps(self) -> int:
         return sum(2 if op == _cabi.MUX else 1 for op, _, _ in self._gates if op not in _FREE)
+
+    def _schedule(self) -> List[int]:
+        """Final level of every wire.  A gate may sit anywhere between its ASAP level and the level its consumers
+        allow; every (level, opcode) pair costs one launch, and a launch of a few gates costs a full bootstrap
+        latency, so gates with slack are moved to the level inside their window that already holds the largest
+        batch of the same opcode (ripple-carry adder: all propagate XORs at level 1, all sum XORs at the last
+        level, instead of one XOR launch beside every carry MUX).  Gates that feed NOT/CONSTANT stay ASAP."""
+        asap = list(self._level)
+        depth = self.depth
+        consumers: Dict[int, List[int]] = {}
+        producer_gate: Dict[int, Tuple[int, Tuple[int, ...]]] = {}
+        for op, idx, w in self._gates:
+            producer_gate[w] = (op, idx)
+            for i in idx:
+                consumers.setdefault(i, []).append(w)
+        # ALAP by a reverse pass (wires are numbered in creation order, so consumers have larger indices)
+        alap = [depth] * self._nwires
+        for w in range(self._nwires - 1, -1, -1):
+            for c in consumers.get(w, []):
+                cop = producer_gate[c][0]
+                alap[w] = min(alap[w], alap[c] if cop in _FREE else alap[c] - 1)
+        movable = [w for w, (op, _) in producer_gate.items()
+                   if op not in _FREE and not any(producer_gate[c][0] in _FREE for c in consumers.get(w, []))]
+        level = list(asap)
+        placed = [True] * self._nwires
+        for w in movable:
+            placed[w] = alap[w] == asap[w]
+        groups: Dict[Tuple[int, int], int] = {}
+        for w, (op, _) in producer_gate.items():
+            if placed[w] and op not in _FREE:
+                groups[(level[w], op)] = groups.get((level[w], op), 0) + 1
+        for w in sorted((w for w in movable if not placed[w]), key=lambda w: (alap[w] - asap[w], asap[w], w)):
+            op, idx = producer_gate[w]
+            lo = max([level[i] if placed[i] else asap[i] for i in idx], default=0) + 1
+            hi = min([(level[c] if placed[c] else asap[c]) - 1 for c in consumers.get(w, [])], default=depth)
+            best = max(range(lo, hi + 1), key=lambda L: (groups.get((L, op), 0), -L))
+            level[w], placed[w] = best, True
+            groups[(best, op)] = groups.get((best, op), 0) + 1
+        return level
 
     def levels(self) -> List[List[Tuple[int, np.ndarray, np.ndarray]]]:
         """Per level, a list of (op, operand wire indices [arity][count], output wire indices [count]).
@@ -95,8 +139,9 @@ class Circuit:
         in creation order (a NOT of a NOT stays ordered)."""
         by_level: Dict[int, Dict[int, List[Tuple[Tuple[int, ...], int]]]] = {}
         free_by_level: Dict[int, List[Tuple[int, Tuple[int, ...], int]]] = {}
+        sched = self._schedule()
         for op, idx, w in self._gates:
-            lvl = self._level[w]
+            lvl = sched[w]
             if op in _FREE:
                 free_by_level.setdefault(lvl, []).append((op, idx, w))
             else:
