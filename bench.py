@@ -174,6 +174,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's version banner off stdout: stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # ---- replicated keys (every rank derives the same key set; no key traffic between GPUs)
