@@ -49,6 +49,10 @@ struct tfhe_b200_ctx {
     int ksk_stride = 0;
     bool have_bk = false, have_ksk = false;
     DevBuf bx, by, bz, bout, bu1, bu2, bidx, bidx2;
+    // second staging slot + copy streams of the host-buffer entry points (host_chunks double-buffers its chunks)
+    DevBuf bx2, by2, bz2, bout2;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     // The scratch buffers above are shared by every entry point.  Calls are stream-ordered on the stream they are
     // given, so a call on a DIFFERENT stream than the previous user first waits for that user's event.
     cudaEvent_t scratch_ev = nullptr;
@@ -338,6 +342,13 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
     ctx = c;
     cudaError_t e = cudaEventCreateWithFlags(&c->scratch_ev, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+        e = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) { delete c; return fail(nullptr, TFHE_B200_ECUDA, cudaGetErrorString(e)); }
     // twiddle table E[x] = exp(-i*pi*x/1024), computed in long double
     std::vector<double2> E(2048);
@@ -356,8 +367,13 @@ void tfhe_b200_destroy(tfhe_b200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->copy_in) { cudaStreamSynchronize(c->copy_in); cudaStreamDestroy(c->copy_in); }
+    if (c->copy_out) { cudaStreamSynchronize(c->copy_out); cudaStreamDestroy(c->copy_out); }
+    for (int i = 0; i < 2; i++)
+        for (cudaEvent_t ev : {c->ev_in[i], c->ev_done[i], c->ev_out[i]})
+            if (ev) cudaEventDestroy(ev);
     if (c->scratch_ev) cudaEventDestroy(c->scratch_ev);
-    for (DevBuf* b : {&c->bx, &c->by, &c->bz, &c->bout, &c->bu1, &c->bu2, &c->bidx, &c->bidx2})
+    for (DevBuf* b : {&c->bx, &c->by, &c->bz, &c->bout, &c->bu1, &c->bu2, &c->bidx, &c->bidx2, &c->bx2, &c->by2, &c->bz2, &c->bout2})
         if (b->p) cudaFree(b->p);
     if (c->d_E) cudaFree(c->d_E);
     if (c->d_bk_fft) cudaFree(c->d_bk_fft);
@@ -461,26 +477,46 @@ int tfhe_b200_keyswitch_batch_dev(tfhe_b200_ctx* ctx, const int32_t* in, int32_t
 
 // ---- single-key, host buffers -----------------------------------------------------------------------
 // Generic chunked host driver: up to three inputs of widths win, one output of width wout.
+// The chunks are double-buffered: while chunk i computes on ctx->stream, chunk i+1 is copied in on `copy_in` and
+// chunk i-1 is copied out on `copy_out` (events order the three streams per staging slot), so for batches of
+// more than one chunk the PCIe time hides behind the kernels.  Returns after everything has landed in `hout`.
 template <typename F>
 static int host_chunks(tfhe_b200_ctx* ctx, const int32_t* const hin[3], const size_t win[3], int32_t* hout, size_t wout,
                        size_t count, F&& body) {
-    DevBuf* bin[3] = {&ctx->bx, &ctx->by, &ctx->bz};
+    DevBuf* bin[2][3] = {{&ctx->bx, &ctx->by, &ctx->bz}, {&ctx->bx2, &ctx->by2, &ctx->bz2}};
+    DevBuf* bo[2] = {&ctx->bout, &ctx->bout2};
     ScratchGuard guard(ctx, ctx->stream);
-    for (size_t off = 0; off < count; off += ctx->chunk) {
-        size_t cnt = std::min(ctx->chunk, count - off);
+    // a batch that fits one chunk is still cut in (up to) 4 pieces of whole CTA waves so that its copies overlap too
+    const size_t wave = (size_t)4 * ctx->sm_count;
+    size_t chunk = ctx->chunk;
+    if (count <= chunk && count >= 8 * wave) chunk = ((count + 3) / 4 + wave - 1) / wave * wave;
+    bool used[2] = {false, false};
+    size_t idx = 0;
+    for (size_t off = 0; off < count; off += chunk, idx++) {
+        const int slot = (int)(idx & 1);
+        const size_t cnt = std::min(chunk, count - off);
         int rc;
         int32_t* din[3] = {nullptr, nullptr, nullptr};
+        if (used[slot]) CU(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_done[slot], 0));   // inputs of chunk idx-2 consumed
         for (int a = 0; a < 3; a++) {
             if (!hin[a]) continue;
-            if ((rc = reserve(ctx, *bin[a], cnt * win[a] * 4))) return rc;
-            din[a] = (int32_t*)bin[a]->p;
-            CU(cudaMemcpyAsync(din[a], hin[a] + off * win[a], cnt * win[a] * 4, cudaMemcpyHostToDevice, ctx->stream));
+            if ((rc = reserve(ctx, *bin[slot][a], std::min(chunk, count) * win[a] * 4))) return rc;
+            din[a] = (int32_t*)bin[slot][a]->p;
+            CU(cudaMemcpyAsync(din[a], hin[a] + off * win[a], cnt * win[a] * 4, cudaMemcpyHostToDevice, ctx->copy_in));
         }
-        if ((rc = reserve(ctx, ctx->bout, cnt * wout * 4))) return rc;
-        if ((rc = body(din[0], din[1], din[2], (int32_t*)ctx->bout.p, cnt))) return rc;
-        CU(cudaMemcpyAsync(hout + off * wout, ctx->bout.p, cnt * wout * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaEventRecord(ctx->ev_in[slot], ctx->copy_in));
+        if ((rc = reserve(ctx, *bo[slot], std::min(chunk, count) * wout * 4))) return rc;
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[slot], 0));
+        if (used[slot]) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[slot], 0));     // output of chunk idx-2 copied out
+        if ((rc = body(din[0], din[1], din[2], (int32_t*)bo[slot]->p, cnt))) return rc;
+        CU(cudaEventRecord(ctx->ev_done[slot], ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[slot], 0));
+        CU(cudaMemcpyAsync(hout + off * wout, bo[slot]->p, cnt * wout * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
+        CU(cudaEventRecord(ctx->ev_out[slot], ctx->copy_out));
+        used[slot] = true;
     }
+    CU(cudaStreamSynchronize(ctx->copy_out));
+    CU(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
