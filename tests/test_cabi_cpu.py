@@ -92,3 +92,21 @@ def test_host_keyswitch_key_matches_reference_semantics():
     msg = api._wrap((in_key[:, None, None].astype(np.int64) * h) << (32 - 2 * j)).astype(np.int64)
     err = ((ph - msg + 2 ** 31) % 2 ** 32 - 2 ** 31) / 2 ** 32
     assert np.abs(err).max() < 2e-4
+
+
+def test_secret_key_and_ciphertext_files_round_trip(tmp_path):
+    """The .npz key / ciphertext files (host logic; the cloud-key file needs a GPU and is tested there)."""
+    import numpy as np
+    import tfhe_jl_b200 as T
+    rng = np.random.default_rng(3)
+    sk = T.SecretKey(rng, T.tfhe_parameters_128())
+    T.save_secret_key(tmp_path / "sk.npz", sk)
+    sk2 = T.load_secret_key(tmp_path / "sk.npz")
+    assert sk2.params == sk.params and np.array_equal(sk2.key, sk.key)
+    ct = T.encrypt(rng, sk, [True, False, True])
+    T.save_ciphertext(tmp_path / "ct.npz", ct)
+    ct2 = T.load_ciphertext(tmp_path / "ct.npz")
+    assert np.array_equal(ct2.data, ct.data) and list(T.decrypt(sk2, ct2)) == [True, False, True]
+    import pytest
+    with pytest.raises(ValueError):
+        T.load_secret_key(tmp_path / "ct.npz")

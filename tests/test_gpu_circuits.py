@@ -89,3 +89,12 @@ def test_levelised_adder32(keypair):
     x, y = 0xDEADBEEF, 0x12345678
     out = adder_circuit(32).run(ck, {"a": T.encrypt(rng, sk, bits_of(x, 32)), "b": T.encrypt(rng, sk, bits_of(y, 32))})
     assert sum(int(v) << i for i, v in enumerate(T.decrypt(sk, out["sum"].to_host()))) == (x + y) & 0xFFFFFFFF
+
+
+def test_cloud_key_file_round_trip(keypair, tmp_path):
+    """A saved cloud key reloaded into a fresh context evaluates to the same ciphertexts."""
+    rng, sk, ck = keypair
+    T.save_cloud_key(tmp_path / "ck.npz", ck)
+    ck2 = T.load_cloud_key(tmp_path / "ck.npz")
+    x, y = T.encrypt(rng, sk, [True, False, True, False]), T.encrypt(rng, sk, [True, True, False, False])
+    assert np.array_equal(T.gate_nand(ck2, x, y).data, T.gate_nand(ck, x, y).data)

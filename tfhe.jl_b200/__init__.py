@@ -18,3 +18,5 @@ from .api import (CloudKey, CloudKeyPart, DeviceLweBatch, LweSample, constant_de
 __all__ = [n for n in dir() if not n.startswith("_")]
 
 from .circuit import Circuit, Wire, adder_circuit, minimum_circuit  # noqa: E402,F401
+from .api import (load_ciphertext, load_cloud_key, load_secret_key, save_ciphertext, save_cloud_key,  # noqa: E402,F401
+                  save_secret_key)

@@ -435,3 +435,67 @@ def constant_dev(ck: CloudKey, values) -> DeviceLweBatch:
     flags = torch.zeros((v.size, ck.params.lwe_size + 1), dtype=torch.int32)
     flags[:, 0] = torch.from_numpy(v.astype(np.int32))
     return gate_dev(ck, _cabi.CONSTANT, DeviceLweBatch(flags.cuda()))
+
+
+# ------------------------------------------------------------------ binary key / ciphertext files
+# The reference has no wire format.  These are numpy `.npz` archives holding the int32 arrays in exactly the
+# layouts of the C ABI (include/tfhe_b200.h), plus the parameter tuple, so a key generated once — here, or exported
+# from a real TFHE.jl install by julia/crosscheck.jl's conversion — can be reloaded onto any GPU without keygen.
+_FORMAT = "tfhe-b200/1"
+
+
+def _params_array(p: SchemeParameters) -> np.ndarray:
+    return np.array([p.lwe_size, p.lwe_noise_stddev, p.tlwe_polynomial_degree, p.tlwe_mask_size, p.bs_decomp_length,
+                     p.bs_log2_base, p.bs_noise_stddev, p.ks_decomp_length, p.ks_log2_base, p.ks_noise_stddev,
+                     p.max_parties], dtype=np.float64)
+
+
+def _params_from(a: np.ndarray) -> SchemeParameters:
+    f = [float(v) for v in a]
+    return SchemeParameters(int(f[0]), f[1], int(f[2]), int(f[3]), int(f[4]), int(f[5]), f[6], int(f[7]), int(f[8]), f[9], int(f[10]))
+
+
+def _check_format(z, kind: str):
+    if str(z["format"]) != _FORMAT or str(z["kind"]) != kind:
+        raise ValueError(f"not a {kind} file of format {_FORMAT}")
+
+
+def save_secret_key(path, key: SecretKey):
+    np.savez(path, format=_FORMAT, kind="secret_key", params=_params_array(key.params), key=key.key.astype(np.int32))
+
+
+def load_secret_key(path) -> SecretKey:
+    with np.load(path) as z:
+        _check_format(z, "secret_key")
+        sk = SecretKey.__new__(SecretKey)
+        sk.params, sk.key = _params_from(z["params"]), z["key"].astype(np.int32)
+        return sk
+
+
+def save_cloud_key(path, ck: CloudKey):
+    np.savez(path, format=_FORMAT, kind="cloud_key", params=_params_array(ck.params),
+             bootstrap_key=ck.bootstrap_key, keyswitch_key=ck.keyswitch_key)
+
+
+def load_cloud_key(path, device: int = 0, flags: int = _cabi.FLAG_SPLIT_FFT) -> CloudKey:
+    """Creates the GPU context and loads (transforms) the key on `device`; no key generation."""
+    with np.load(path) as z:
+        _check_format(z, "cloud_key")
+        ck = CloudKey.__new__(CloudKey)
+        ck.params = _params_from(z["params"])
+        ck.bootstrap_key = np.ascontiguousarray(z["bootstrap_key"], dtype=np.int32)
+        ck.keyswitch_key = np.ascontiguousarray(z["keyswitch_key"], dtype=np.int32)
+    ck.ctx = _context(ck.params, 1, device, flags)
+    ck.ctx.load_bk(ck.bootstrap_key)
+    ck.ctx.load_ksk(ck.keyswitch_key)
+    return ck
+
+
+def save_ciphertext(path, sample: LweSample):
+    np.savez(path, format=_FORMAT, kind="lwe", data=sample.data.astype(np.int32), variance=np.float64(sample.current_variance))
+
+
+def load_ciphertext(path) -> LweSample:
+    with np.load(path) as z:
+        _check_format(z, "lwe")
+        return LweSample(z["data"].astype(np.int32), float(z["variance"]))
