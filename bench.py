@@ -36,6 +36,7 @@ sys.path.insert(0, ROOT)
 W_FFT_FLOP_PER_GATE = 94.72e6      # n * 189 440 FP64 flop, FFT formulation (what the reference computes)
 Q_KSK_BYTES_PER_GATE = 12_312_576  # KSK bytes gathered per gate
 METRIC = "bootstrapped NAND gates/s"
+OUT = sys.stdout
 
 
 def parse():
@@ -125,7 +126,8 @@ def run_reference(args, rank, world):
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "batched NAND gate bootstrap, 80-bit params (n=500, N=1024, k=1, l=2, Bg=2^10)", "sample": desc},
                 "cpu_baseline": {"value": j["gates_per_s"], "unit": "gates/s", "cores": j["cores"], "kind": "reference", "sample": desc},
-                "e2e": {"value": j["gates_per_s"], "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+                "e2e": {"value": j["gates_per_s"], "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}),
+                file=OUT, flush=True)
             return
         except (IndexError, KeyError, ValueError):
             pass   # fall through to the port
@@ -151,10 +153,16 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": "gates/s", "cores": cores, "kind": "port", "sample": sample_desc},
         "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }), file=OUT, flush=True)
 
 
 def main():
+    # stdout carries exactly ONE JSON line: keep a private handle on the real stdout and point fd 1 at stderr, so
+    # that anything a library writes to stdout (NCCL prints its version banner there) cannot pollute it
+    global OUT
+    sys.stdout.flush()
+    OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -174,7 +182,6 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's version banner off stdout: stdout carries ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # ---- replicated keys (every rank derives the same key set; no key traffic between GPUs)
@@ -328,7 +335,7 @@ def main():
             assert np.array_equal(ref, got[:sample]), "GPU ciphertexts differ from the oracle"
             line["cpu_baseline"] = {"value": sample / dt, "unit": "gates/s", "cores": cores, "kind": "port", "seconds": dt,
                                     "sample": f"first {sample} gates of the step's batch, one gate per OpenMP thread; GPU outputs bit-identical on this sample"}
-        print(json.dumps(line))
+        print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
