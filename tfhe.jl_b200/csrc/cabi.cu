@@ -48,7 +48,7 @@ struct tfhe_b200_ctx {
     int32_t* d_ksk = nullptr;        // [parties][Nk][t][base-1][stride]
     int ksk_stride = 0;
     bool have_bk = false, have_ksk = false;
-    DevBuf bx, by, bz, bout, bu1, bu2, bidx, bidx2;
+    DevBuf bx, by, bz, bout, bu1, bidx, bidx2;
     // second staging slot + copy streams of the host-buffer entry points (host_chunks double-buffers its chunks)
     DevBuf bx2, by2, bz2, bout2;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
@@ -271,9 +271,9 @@ int bootstrap_wo_ks_dev(tfhe_b200_ctx* ctx, const int32_t* x, const int32_t* y, 
     return launch_br<0>(ctx, A, s);
 }
 
-// one gate over device-resident ciphertexts; u1/u2 are scratch [count][Nk+1]
+// one gate over device-resident ciphertexts; u1 is scratch [count][Nk+1] ([2*count][Nk+1] for MUX)
 int gate_dev(tfhe_b200_ctx* ctx, int op, const int32_t* x, const int32_t* y, const int32_t* z, int32_t* out,
-             size_t count, int32_t* u1, int32_t* u2, cudaStream_t s) {
+             size_t count, int32_t* u1, cudaStream_t s) {
     const int w = ctx->P.n + 1, wu = ctx->P.N * ctx->P.k + 1;
     int32_t cb, ka, kb;
     int rc;
@@ -298,7 +298,6 @@ int gate_dev(tfhe_b200_ctx* ctx, int op, const int32_t* x, const int32_t* y, con
                 A.mu = kMu8; A.out = u1;
                 if ((rc = launch_br<0>(ctx, A, s))) return rc;
             }
-            (void)u2;
             if ((rc = launch_lincomb(ctx, u1, u1 + count * (size_t)wu, u1, 1, 1, kMu8, wu, count, 0, s))) return rc;   // gates.jl:174
             return launch_keyswitch(ctx, u1, out, count, s);                                          // gates.jl:176
         default:
@@ -373,7 +372,7 @@ void tfhe_b200_destroy(tfhe_b200_ctx* c) {
         for (cudaEvent_t ev : {c->ev_in[i], c->ev_done[i], c->ev_out[i]})
             if (ev) cudaEventDestroy(ev);
     if (c->scratch_ev) cudaEventDestroy(c->scratch_ev);
-    for (DevBuf* b : {&c->bx, &c->by, &c->bz, &c->bout, &c->bu1, &c->bu2, &c->bidx, &c->bidx2, &c->bx2, &c->by2, &c->bz2, &c->bout2})
+    for (DevBuf* b : {&c->bx, &c->by, &c->bz, &c->bout, &c->bu1, &c->bidx, &c->bidx2, &c->bx2, &c->by2, &c->bz2, &c->bout2})
         if (b->p) cudaFree(b->p);
     if (c->d_E) cudaFree(c->d_E);
     if (c->d_bk_fft) cudaFree(c->d_bk_fft);
@@ -457,7 +456,7 @@ int tfhe_b200_gate_batch_dev(tfhe_b200_ctx* ctx, int op, const int32_t* x, const
     const size_t wu = (size_t)ctx->P.N * ctx->P.k + 1;
     if ((rc = reserve(ctx, ctx->bu1, (op == TFHE_B200_MUX ? 2 : 1) * count * wu * 4))) return rc;
     ScratchGuard guard(ctx, (cudaStream_t)stream);
-    return gate_dev(ctx, op, x, y, z, out, count, (int32_t*)ctx->bu1.p, (int32_t*)ctx->bu2.p, (cudaStream_t)stream);
+    return gate_dev(ctx, op, x, y, z, out, count, (int32_t*)ctx->bu1.p, (cudaStream_t)stream);
 }
 
 int tfhe_b200_bootstrap_wo_ks_batch_dev(tfhe_b200_ctx* ctx, int32_t mu, const int32_t* x, int32_t* out, size_t count,
@@ -532,7 +531,7 @@ int tfhe_b200_gate_batch(tfhe_b200_ctx* ctx, int op, const int32_t* x, const int
     return host_chunks(ctx, hin, win, out, w, count, [&](int32_t* dx, int32_t* dy, int32_t* dz, int32_t* dout, size_t cnt) {
         int r;
         if ((r = reserve(ctx, ctx->bu1, (op == TFHE_B200_MUX ? 2 : 1) * cnt * wu * 4))) return r;
-        return gate_dev(ctx, op, dx, dy, dz, dout, cnt, (int32_t*)ctx->bu1.p, (int32_t*)ctx->bu2.p, ctx->stream);
+        return gate_dev(ctx, op, dx, dy, dz, dout, cnt, (int32_t*)ctx->bu1.p, ctx->stream);
     });
 }
 
