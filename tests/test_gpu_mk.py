@@ -98,3 +98,17 @@ def test_mk_nand_large_batch_ring_configurations(p, count, monkeypatch):
     assert np.array_equal(make_mk_ctx(mk, _cabi.FLAG_UNSPLIT_FFT).mk_nand(x, y), want)
     monkeypatch.setenv("TFHE_B200_MK_RING", "0")
     assert np.array_equal(make_mk_ctx(mk).mk_nand(x, y), want)
+
+
+def test_mk_latency_kernel_agrees_with_ring_kernel(mkkeys2, mkctx2, monkeypatch):
+    """Small 2-party batches take the latency kernel (one gate per CTA, 12 digit polynomials over 6 groups);
+    with TFHE_B200_LOWLAT=0 the same batch goes through the ring kernel (2 gates per CTA).  Same ciphertexts,
+    equal to the oracle's."""
+    rng = O.Rng(31)
+    bits = np.random.default_rng(31).integers(0, 2, (5, 2)).astype(bool)
+    x, y = O.mk_encrypt(rng, mkkeys2, bits[:, 0]), O.mk_encrypt(rng, mkkeys2, bits[:, 1])
+    want = mkctx2.nand(x, y)
+    for flags in (_cabi.FLAG_SPLIT_FFT, _cabi.FLAG_UNSPLIT_FFT):
+        assert np.array_equal(make_mk_ctx(mkkeys2, flags).mk_nand(x, y), want)
+    monkeypatch.setenv("TFHE_B200_LOWLAT", "0")
+    assert np.array_equal(make_mk_ctx(mkkeys2).mk_nand(x, y), want)

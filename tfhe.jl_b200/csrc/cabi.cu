@@ -19,6 +19,7 @@
 #include "blind_rotate_lowlat.cuh"
 #include "mk_kernels.cuh"
 #include "mk_blind_rotate.cuh"
+#include "mk_blind_rotate_lowlat.cuh"
 
 using namespace tfhe_b200;
 
@@ -187,6 +188,15 @@ int launch_extern(tfhe_b200_ctx* ctx, const int32_t* acc, const int32_t* idx, in
     return 0;
 }
 
+// latency path: several CTAs per ciphertext; the output rows must have been zero-initialised by the caller
+int launch_keyswitch_sliced(tfhe_b200_ctx* ctx, const KeyswitchArgs& A, size_t count, cudaStream_t s) {
+    const int slices = (int)std::min<size_t>(32, std::max<size_t>(1, (size_t)16 * ctx->sm_count / count));
+    keyswitch_sliced_kernel<<<(unsigned)(count * slices), A.stride / 4, (size_t)(A.Nk / slices + 1) * sizeof(int32_t), s>>>(A, count, slices);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
 int launch_keyswitch_args(tfhe_b200_ctx* ctx, const KeyswitchArgs& A, size_t count, cudaStream_t s) {
     keyswitch_kernel<<<(unsigned)count, A.stride / 4, (size_t)A.Nk * sizeof(int32_t), s>>>(A, count);
     CU(cudaGetLastError());
@@ -204,13 +214,8 @@ int launch_keyswitch(tfhe_b200_ctx* ctx, const int32_t* in, int32_t* out, size_t
     A.in_stride = A.Nk + 1; A.in_offset = 0; A.in_b_offset = A.Nk;
     A.out_stride = P.n + 1; A.out_offset = 0; A.b_offset = P.n; A.b_mode = 0;
     if (count <= 3 * (size_t)ctx->sm_count && ctx->lowlat) {
-        // latency path: several CTAs per ciphertext (keyswitch_sliced_kernel)
-        const int slices = (int)std::min<size_t>(32, std::max<size_t>(1, (size_t)16 * ctx->sm_count / count));
         CU(cudaMemsetAsync(out, 0, count * (size_t)(P.n + 1) * sizeof(int32_t), s));
-        keyswitch_sliced_kernel<<<(unsigned)(count * slices), A.stride / 4, (size_t)(A.Nk / slices + 1) * sizeof(int32_t), s>>>(A, count, slices);
-        CU(cudaGetLastError());
-        ctx->launches++;
-        return 0;
+        return launch_keyswitch_sliced(ctx, A, count, s);
     }
     return launch_keyswitch_args(ctx, A, count, s);
 }

@@ -322,7 +322,7 @@ __global__ void keyswitch_kernel(KeyswitchArgs A, unsigned long long count) {
 // a 1 024-step chain of L2 round trips.  Here `slices` CTAs share a ciphertext: each gathers a contiguous range of
 // mask positions and adds its partial sums into `out` — zero-initialised by the caller — with integer atomics
 // (integer addition commutes, so the result is the same bits as keyswitch_kernel); slice 0 also adds the input b.
-// Single-key layout only (b_mode 0).
+// b_mode 1 (MK, one launch per party): the joint b was written by the caller, every slice only subtracts.
 __global__ void keyswitch_sliced_kernel(KeyswitchArgs A, unsigned long long count, int slices) {
     extern __shared__ int32_t s_a[];
     const size_t g = blockIdx.x / slices;
@@ -359,7 +359,7 @@ __global__ void keyswitch_sliced_kernel(KeyswitchArgs A, unsigned long long coun
         if (c < A.n) atomicAdd(o + c, vals[e]);
         else if (c == A.n) {
             uint32_t v = vals[e];
-            if (sl == 0) v += (uint32_t)A.in[g * A.in_stride + A.in_b_offset];
+            if (sl == 0 && A.b_mode == 0) v += (uint32_t)A.in[g * A.in_stride + A.in_b_offset];   // b_mode 1: b was copied by the caller
             atomicAdd(reinterpret_cast<unsigned int*>(A.out_b + g * A.out_stride + A.b_offset), v);
         }
     }
