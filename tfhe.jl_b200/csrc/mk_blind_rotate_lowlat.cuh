@@ -93,11 +93,12 @@ __global__ void __launch_bounds__(64 * kMkLowlatGroups, 1) mk_blind_rotate_lowla
                      : kind == 1 ? (q < p ? mk_xi(L, p, r, q) : mk_c0i(L, p, r))
                                  : mk_yi(L, p, d, party);
             };
-            if (worker) {   // the expanded key does not fit L2: pull this iteration's spectra in while phase 1 computes
-#pragma unroll
+            if (worker && t == 0) {   // the expanded key does not fit L2: pull this iteration's spectra in (one bulk
+#pragma unroll                 // prefetch of 8 KB per step) while phase 1 computes
                 for (int d = 0; d < ND; d++)
                     if (d < nsteps)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(sample - t + (size_t)key_poly(d) * PS + (size_t)t * 8));
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+                                     ::"l"(sample + (size_t)key_poly(d) * PS), "n"(kSpectrum * 16) : "memory");
             }
             {
                 uint32_t tl[8], th[8];
