@@ -248,8 +248,8 @@ def main():
 
     # ---- end to end through the host-buffer C-ABI call
     step_e2e()
-    t0 = time.perf_counter()
     barrier()
+    t0 = time.perf_counter()      # after the barrier: rank skew from the checks above is not part of the timed region
     for _ in range(args.steps):
         step_e2e()
     barrier()
