@@ -269,3 +269,19 @@ def test_latency_path_can_be_disabled_and_agrees(keys80, gctx80, monkeypatch):
     ctx.load_bk(keys80.bk); ctx.load_ksk(keys80.ksk)
     assert np.array_equal(ctx.gate(O.XOR, x, y), want)            # 150 gates: 2 per CTA
     assert np.array_equal(ctx.gate(O.XOR, x[:3], y[:3]), want[:3])  # 3 gates: 1 per CTA
+
+
+@pytest.mark.parametrize("count", [445, 1000])
+def test_tiled_keyswitch_equals_per_ciphertext_kernel(keys80, gctx80, monkeypatch, count):
+    """Large batches use keyswitch_tile_kernel (64 ciphertexts per CTA, table streamed through shared memory);
+    TFHE_B200_KS_TILE=0 selects the one-CTA-per-ciphertext kernel.  Random dimension-1024 inputs, ragged tiles."""
+    rng = np.random.default_rng(count)
+    u = rng.integers(-2 ** 31, 2 ** 31, (count, 1025), dtype=np.int64).astype(np.int32)
+    got = gctx80.keyswitch(u)
+    monkeypatch.setenv("TFHE_B200_KS_TILE", "0")
+    P = keys80.params
+    ctx = T.Context(n=P.n, l=P.l, bgbit=P.bgbit, t=P.t, basebit=P.basebit)
+    ctx.load_bk(keys80.bk); ctx.load_ksk(keys80.ksk)
+    assert np.array_equal(got, ctx.keyswitch(u))
+    octx = O.Context(keys80)
+    assert np.array_equal(got[:8], octx.keyswitch(u[:8]))

@@ -42,6 +42,7 @@ struct tfhe_b200_ctx {
     int G = 0;                       // gates per CTA of the blind-rotation kernel (0 = default, see launch_br_np)
     int sm_count = 148;
     int lowlat = 1;                  // batches of <= 1 gate per SM: one gate per CTA spread over 4 groups + sliced key switch
+    int ks_tile = 1;                 // large batches: tiled key switch (TFHE_B200_KS_TILE=0: one CTA per ciphertext)
     int mk_ring = 1;                 // MK blind rotation: 1 = TMA key ring, several gates per CTA (mk_blind_rotate.cuh)
     cudaStream_t stream = nullptr;   // used by the host-buffer entry points
     double2* d_E = nullptr;          // exp(-i*pi*x/1024), x < 2048
@@ -198,6 +199,22 @@ int launch_keyswitch_sliced(tfhe_b200_ctx* ctx, const KeyswitchArgs& A, size_t c
 }
 
 int launch_keyswitch_args(tfhe_b200_ctx* ctx, const KeyswitchArgs& A, size_t count, cudaStream_t s) {
+    // large batches: 64 ciphertexts per CTA, table streamed once per CTA through shared memory (keyswitch_tile_kernel)
+    if (ctx->ks_tile && A.t == kKsT && A.basebit == kKsBasebit && (A.stride == 512 || A.stride == 640) &&
+        count > 3 * (size_t)ctx->sm_count) {
+        const size_t smem = ks_tile_smem_bytes(A.stride);
+        const unsigned grid = (unsigned)((count + kKsTile - 1) / kKsTile);
+        if (A.stride == 512) {
+            CU(cudaFuncSetAttribute(keyswitch_tile_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            keyswitch_tile_kernel<512><<<grid, 256, smem, s>>>(A, count);
+        } else {
+            CU(cudaFuncSetAttribute(keyswitch_tile_kernel<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            keyswitch_tile_kernel<640><<<grid, 320, smem, s>>>(A, count);
+        }
+        CU(cudaGetLastError());
+        ctx->launches++;
+        return 0;
+    }
     keyswitch_kernel<<<(unsigned)count, A.stride / 4, (size_t)A.Nk * sizeof(int32_t), s>>>(A, count);
     CU(cudaGetLastError());
     ctx->launches++;
@@ -341,6 +358,7 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
     c->G = env_int("TFHE_B200_G", 0);
     c->mk_ring = env_int("TFHE_B200_MK_RING", 1);
     c->lowlat = env_int("TFHE_B200_LOWLAT", 1);
+    c->ks_tile = env_int("TFHE_B200_KS_TILE", 1);
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) c->sm_count = prop.multiProcessorCount; }
     c->chunk = (size_t)env_int("TFHE_B200_CHUNK", 1 << 16);
     ctx = c;
