@@ -15,17 +15,16 @@ timeout 300 python tools/circuit_latency.py > gpurun_out/circuits_split.json 2> 
 FLAGS=1 CPU=0 timeout 300 python tools/circuit_latency.py > gpurun_out/circuits_unsplit.json 2>> gpurun_out/circuits.err
 FLAGS=1 timeout 300 python tools/mk_perf.py 2 2368 > gpurun_out/mk_perf_p2_unsplit.json 2> gpurun_out/mk_perf.err
 timeout 300 python tools/mk_perf.py 4 1184 > gpurun_out/mk_perf_p4.json 2>> gpurun_out/mk_perf.err
-timeout 600 python tools/mk_perf.py 8 592 > gpurun_out/mk_perf_p8.json 2>> gpurun_out/mk_perf.err
 timeout 900 python tools/sweep.py > gpurun_out/sweep.json 2> gpurun_out/sweep.err
 
 NCU="ncu --set full --clock-control none -f"
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"   # the default workload (2^16 gates per launch)
 $CMD > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 $CMD > gpurun_out/plain2.log 2>&1 && $NCU -k regex:blind_rotate_kernel -s 1 -c 1 -o gpurun_out/prof_blind_rotate $CMD > gpurun_out/ncu_full.log 2>&1
-CMD2="python tools/latency_probe.py"
-$CMD2 > gpurun_out/latency.json 2> gpurun_out/latency.err && $NCU -k regex:blind_rotate_lowlat -s 2 -c 1 -o gpurun_out/prof_lowlat $CMD2 > gpurun_out/ncu_full_lowlat.log 2>&1
-CMD3="python tools/mk_perf.py 2 2368"
-$CMD3 > gpurun_out/mk_perf_p2.json 2>> gpurun_out/mk_perf.err && $NCU -k regex:mk_blind_rotate_ring -s 1 -c 1 -o gpurun_out/prof_mk_ring $CMD3 > gpurun_out/ncu_full_mk.log 2>&1
+$CMD > gpurun_out/plain3.log 2>&1 && $NCU -k regex:keyswitch_tile -s 1 -c 1 -o gpurun_out/prof_keyswitch_tile $CMD > gpurun_out/ncu_full_ks.log 2>&1
+timeout 300 python tools/latency_probe.py > gpurun_out/latency.json 2> gpurun_out/latency.err
+timeout 300 python tools/mk_perf.py 2 2368 > gpurun_out/mk_perf_p2.json 2>> gpurun_out/mk_perf.err
+timeout 300 python tools/mk_perf.py 2 8 > gpurun_out/mk_perf_p2_small.json 2>> gpurun_out/mk_perf.err
 
 tail -3 gpurun_out/pytest_gpu.log 2>/dev/null; cat gpurun_out/smoke.log 2>/dev/null
 cat gpurun_out/bench_split.json gpurun_out/bench_unsplit.json gpurun_out/bench_reference.json | cut -c1-400
