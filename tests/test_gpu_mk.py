@@ -112,3 +112,16 @@ def test_mk_latency_kernel_agrees_with_ring_kernel(mkkeys2, mkctx2, monkeypatch)
         assert np.array_equal(make_mk_ctx(mkkeys2, flags).mk_nand(x, y), want)
     monkeypatch.setenv("TFHE_B200_LOWLAT", "0")
     assert np.array_equal(make_mk_ctx(mkkeys2).mk_nand(x, y), want)
+
+
+def test_mk_keyswitch_tiled_equals_per_ciphertext_kernel(monkeypatch):
+    """mk_keyswitch (mk_internals.jl:397-411) on a batch large enough for the tiled kernel (one launch per party,
+    the joint b accumulated with integer atomics) against the one-CTA-per-ciphertext kernel and the oracle."""
+    p = 2
+    mk = O.mk_keygen(O.small_params(O.MK_PARAMS[p], 3), p, 90)
+    count = 4100
+    u = np.random.default_rng(5).integers(-2 ** 31, 2 ** 31, (count, p * N + 1), dtype=np.int64).astype(np.int32)
+    got = make_mk_ctx(mk).keyswitch(u)
+    monkeypatch.setenv("TFHE_B200_KS_TILE", "0")
+    assert np.array_equal(got, make_mk_ctx(mk).keyswitch(u))
+    assert np.array_equal(got[-4:], O.MKContext(mk).keyswitch(u[-4:]))

@@ -200,8 +200,9 @@ int launch_keyswitch_sliced(tfhe_b200_ctx* ctx, const KeyswitchArgs& A, size_t c
 
 int launch_keyswitch_args(tfhe_b200_ctx* ctx, const KeyswitchArgs& A, size_t count, cudaStream_t s) {
     // large batches: 64 ciphertexts per CTA, table streamed once per CTA through shared memory (keyswitch_tile_kernel)
-    if (ctx->ks_tile && A.t == kKsT && A.basebit == kKsBasebit && (A.stride == 512 || A.stride == 640) &&
-        count > 3 * (size_t)ctx->sm_count) {
+    // (a tile of 64 ciphertexts takes ~3.3 ms whatever the batch; the per-ciphertext kernel needs 0.89 us per
+    // ciphertext, so the tile kernel wins from ~4 000 ciphertexts up and fills the GPU from 64 x 148)
+    if (ctx->ks_tile && A.t == kKsT && A.basebit == kKsBasebit && (A.stride == 512 || A.stride == 640) && count >= 4096) {
         const size_t smem = ks_tile_smem_bytes(A.stride);
         const unsigned grid = (unsigned)((count + kKsTile - 1) / kKsTile);
         if (A.stride == 512) {
