@@ -20,14 +20,15 @@ from oracle import oracle as O  # noqa: E402  (synthetic keys / inputs and the d
 
 def main():
     sizes = [int(s) for s in (sys.argv[1:] or ["1024", "4096", "16384", "65536", "262144", "1048576"])]
-    keys = O.keygen(O.PARAMS_80, 123)
+    pset = os.environ.get("PARAMS", "80")
+    keys = O.keygen(O.PARAMS_128 if pset == "128" else O.PARAMS_80, 123)
     P = keys.params
     base = 4096
     bits = np.random.default_rng(0).integers(0, 2, (base, 2)).astype(bool)
     rng = O.Rng(1)
     bx, by = O.encrypt(rng, keys, bits[:, 0]), O.encrypt(rng, keys, bits[:, 1])
     want = ~(bits[:, 0] & bits[:, 1])
-    res = {"workload": "NAND, 80-bit parameters, fresh ciphertexts tiled from a 4096-gate base batch", "rows": []}
+    res = {"workload": f"NAND, {pset}-bit parameters (n={P.n}, l={P.l}, Bg=2^{P.bgbit}), fresh ciphertexts tiled from a 4096-gate base batch", "rows": []}
     for flags, mode in ((0, "split"), (1, "unsplit")):
         ctx = T.Context(n=P.n, l=P.l, bgbit=P.bgbit, t=P.t, basebit=P.basebit, flags=flags)
         ctx.load_bk(keys.bk); ctx.load_ksk(keys.ksk)
