@@ -70,19 +70,21 @@ template <bool INV> __device__ __forceinline__ void dft8(double2 (&a)[8]) {
     double2 s1 = cadd(a[1], a[5]), d1 = csub(a[1], a[5]);
     double2 s2 = cadd(a[2], a[6]), d2 = csub(a[2], a[6]);
     double2 s3 = cadd(a[3], a[7]), d3 = csub(a[3], a[7]);
-    // d_m *= W8^m
+    // d_m *= W8^m.  W8^1 and W8^3 are (+-1 +- i)/sqrt(2): the factor h is not applied here but folded into the
+    // last butterfly as an FMA (a = f +- h*g), which saves the four multiplications.
     if (!INV) {
-        d1 = make_double2((d1.x + d1.y) * h, (d1.y - d1.x) * h);
-        d3 = make_double2((d3.y - d3.x) * h, -(d3.x + d3.y) * h);
+        d1 = make_double2(d1.x + d1.y, d1.y - d1.x);
+        d3 = make_double2(d3.y - d3.x, -(d3.x + d3.y));
     } else {
-        d1 = make_double2((d1.x - d1.y) * h, (d1.x + d1.y) * h);
-        d3 = make_double2(-(d3.x + d3.y) * h, (d3.x - d3.y) * h);
+        d1 = make_double2(d1.x - d1.y, d1.x + d1.y);
+        d3 = make_double2(-(d3.x + d3.y), d3.x - d3.y);
     }
     d2 = rot90<INV>(d2);
     double2 e0 = cadd(s0, s2), e1 = csub(s0, s2), o0 = cadd(s1, s3), o1 = rot90<INV>(csub(s1, s3));
-    double2 f0 = cadd(d0, d2), f1 = csub(d0, d2), g0 = cadd(d1, d3), g1 = rot90<INV>(csub(d1, d3));
+    double2 f0 = cadd(d0, d2), f1 = csub(d0, d2), g0 = cadd(d1, d3), g1 = rot90<INV>(csub(d1, d3));   // g0, g1 unscaled
     a[0] = cadd(e0, o0); a[4] = csub(e0, o0); a[2] = cadd(e1, o1); a[6] = csub(e1, o1);
-    a[1] = cadd(f0, g0); a[5] = csub(f0, g0); a[3] = cadd(f1, g1); a[7] = csub(f1, g1);
+    a[1] = make_double2(fma(h, g0.x, f0.x), fma(h, g0.y, f0.y)); a[5] = make_double2(fma(-h, g0.x, f0.x), fma(-h, g0.y, f0.y));
+    a[3] = make_double2(fma(h, g1.x, f1.x), fma(h, g1.y, f1.y)); a[7] = make_double2(fma(-h, g1.x, f1.x), fma(-h, g1.y, f1.y));
 }
 
 // exp(-i*pi*m/16), m = 0..7: the thread-independent part of the twist
