@@ -15,7 +15,12 @@
  *   - all torus data are int32 (Torus32 = Int32, numeric-functions.jl:1), wrap-around mod 2^32.
  *   - the caller owns every host buffer; the library owns device memory.  Host pointers may be
  *     pageable.  *_dev variants take DEVICE pointers (inputs already resident in HBM) and a
- *     cudaStream_t passed as void* (NULL = default stream); they are asynchronous.
+ *     cudaStream_t passed as void* (NULL = default stream); they are asynchronous and stream-ordered:
+ *     the library's scratch buffers are shared by all calls of a context, and a call given a different
+ *     stream than the previous one first waits (on the device) for that call's work.
+ *   - the kernel shape is chosen per call from `count`: up to 3 gates per SM a latency kernel (one gate per
+ *     CTA) and a sliced key switch, above that 4 gates per CTA, from 4 096 ciphertexts a tiled key switch;
+ *     the results do not depend on the choice.
  *   - there is NO CPU fallback: without a CUDA device every call fails with TFHE_B200_ENODEV.
  *   - calls on one context are serialised by an internal mutex; contexts are independent
  *     (one context per GPU; gate batches shard across contexts with no collective).
