@@ -114,14 +114,87 @@ def test_mk_latency_kernel_agrees_with_ring_kernel(mkkeys2, mkctx2, monkeypatch)
     assert np.array_equal(make_mk_ctx(mkkeys2).mk_nand(x, y), want)
 
 
-def test_mk_keyswitch_tiled_equals_per_ciphertext_kernel(monkeypatch):
-    """mk_keyswitch (mk_internals.jl:397-411) on a batch large enough for the tiled kernel (one launch per party,
-    the joint b accumulated with integer atomics) against the one-CTA-per-ciphertext kernel and the oracle."""
+def random_mk_keys(p, n, seed):
+    """Key-shaped random material (uniform torus words, binary LWE keys).  Ciphertext parity does not need a valid key:
+    the arithmetic is the same, and every operand reaches full magnitude.  Saves the oracle's 53 s 8-party keygen."""
+    P = O.small_params(O.MK_PARAMS[p], n)
+    rng = np.random.default_rng(seed)
+    bk = rng.integers(-2 ** 31, 2 ** 31, (p, P.n, P.l * (2 * p + 2), N), dtype=np.int64).astype(np.int32)
+    ksk = rng.integers(-2 ** 31, 2 ** 31, (p,) + P.ksk_shape, dtype=np.int64).astype(np.int32)
+    lwe = rng.integers(0, 2, (p, P.n)).astype(np.int32)
+    return O.MKKeySet(P, p, lwe, bk, ksk, rng.integers(0, 2, (p, N)).astype(np.int32))
+
+
+def sm_count():
+    import torch
+    return torch.cuda.get_device_properties(0).multi_processor_count
+
+
+def test_mk_keyswitch_tiled_full_size_equals_per_ciphertext_kernel_and_oracle(monkeypatch):
+    """mk_keyswitch (mk_internals.jl:397-411) at n = 500 (table stride 512), so that batches of 4 096 and more really
+    take keyswitch_tile_kernel in its MK mode (one launch per party, non-zero in/out offsets, the joint b accumulated
+    with integer atomics).  Compared with the one-CTA-per-ciphertext kernel (TFHE_B200_KS_TILE=0) on every row and
+    with the oracle on the first and the last (ragged tile) rows."""
     p = 2
-    mk = O.mk_keygen(O.small_params(O.MK_PARAMS[p], 3), p, 90)
+    mk = random_mk_keys(p, 500, 90)
     count = 4100
     u = np.random.default_rng(5).integers(-2 ** 31, 2 ** 31, (count, p * N + 1), dtype=np.int64).astype(np.int32)
     got = make_mk_ctx(mk).keyswitch(u)
     monkeypatch.setenv("TFHE_B200_KS_TILE", "0")
     assert np.array_equal(got, make_mk_ctx(mk).keyswitch(u))
-    assert np.array_equal(got[-4:], O.MKContext(mk).keyswitch(u[-4:]))
+    rows = np.r_[0:4, count - 4:count]
+    assert np.array_equal(got[rows], O.MKContext(mk).keyswitch(u[rows]))
+
+
+def test_keyswitch_tile_stride_640(keys128, monkeypatch):
+    """The 128-bit set (n = 630) pads its table rows to 640 words: the second instantiation of the tile kernel."""
+    P = keys128.params
+    count = 4099
+    u = np.random.default_rng(6).integers(-2 ** 31, 2 ** 31, (count, N + 1), dtype=np.int64).astype(np.int32)
+    def ctx():
+        c = T.Context(n=P.n, l=P.l, bgbit=P.bgbit, t=P.t, basebit=P.basebit)
+        c.load_ksk(keys128.ksk)
+        return c
+    got = ctx().keyswitch(u)
+    monkeypatch.setenv("TFHE_B200_KS_TILE", "0")
+    assert np.array_equal(got, ctx().keyswitch(u))
+    rows = np.r_[0:4, count - 4:count]
+    assert np.array_equal(got[rows], O.Context(keys128).keyswitch(u[rows]))
+
+
+@pytest.mark.parametrize("p,count,nsample", [(2, None, 16), (4, None, 6), (8, 5, 5)])
+def test_mk_nand_full_size_ring_kernels_equal_oracle(p, count, nsample, monkeypatch):
+    """Full-size (n = 500) parity of the large-batch MK kernels (mk_internals.jl:348-515), judged on ciphertext
+    equality with the oracle, never on decryption (the reference's own 2-party output noise, sigma ~ 0.05, makes an
+    occasional gate decrypt wrongly in the reference too).
+
+      2 parties: 4 x SMs + 1 gates -> mk_blind_rotate_ring_kernel with G = 4 (6-stage ring), last CTA ragged;
+      4 parties: 2 x SMs + 2 gates -> G = 4 with the 3-stage ring;  8 parties: 5 gates (G = 2).
+    A sample that includes the first and the ragged last gates is compared bit for bit with the oracle; ALL gates
+    are compared with the one-gate-per-CTA kernel (TFHE_B200_MK_RING=0), so a wrong ciphertext anywhere shows.
+    2 and 4 parties use real oracle keys (and report how many gates decrypt to NAND), 8 parties key-shaped random
+    material (the oracle's 8-party keygen takes a minute)."""
+    sms = sm_count()
+    if count is None:
+        count = 4 * sms + 1 if p == 2 else 2 * sms + 2
+    real = p < 8
+    mk = O.mk_keygen(O.MK_PARAMS[p], p, 300 + p) if real else random_mk_keys(p, 500, 300 + p)
+    rng = np.random.default_rng(p)
+    if real:
+        bits = rng.integers(0, 2, (count, 2)).astype(bool)
+        orng = O.Rng(p)
+        x, y = O.mk_encrypt(orng, mk, bits[:, 0]), O.mk_encrypt(orng, mk, bits[:, 1])
+    else:
+        x = rng.integers(-2 ** 31, 2 ** 31, (count, p * 500 + 1), dtype=np.int64).astype(np.int32)
+        y = rng.integers(-2 ** 31, 2 ** 31, (count, p * 500 + 1), dtype=np.int64).astype(np.int32)
+    got = make_mk_ctx(mk).mk_nand(x, y)
+    idx = np.unique(np.r_[0:nsample // 2, count - (nsample - nsample // 2):count])
+    want = O.MKContext(mk).nand(x[idx], y[idx])
+    assert np.array_equal(got[idx], want), f"{p}-party ring kernel differs from the oracle"
+    monkeypatch.setenv("TFHE_B200_MK_RING", "0")
+    monkeypatch.setenv("TFHE_B200_LOWLAT", "0")
+    assert np.array_equal(got, make_mk_ctx(mk).mk_nand(x, y)), "ring kernel differs from the one-gate-per-CTA kernel"
+    if real:
+        ok = int(np.sum(O.mk_decrypt(mk, got) == ~(bits[:, 0] & bits[:, 1])))
+        print(f"{p} parties: {ok}/{count} gates decrypt to NAND (oracle sample identical)")
+        assert ok >= 0.9 * count

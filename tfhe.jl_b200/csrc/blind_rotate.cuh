@@ -20,6 +20,7 @@
 #pragma once
 #include "kernels.cuh"
 #include "tmem.cuh"
+#include <type_traits>
 
 namespace tfhe_b200 {
 
@@ -61,7 +62,9 @@ constexpr int kChunkBytes = kChunkElems * 16;     // 16 KB
 // k+STAGES-1 (all groups released it an FFT ago, so the wait on `empty` practically never blocks), which
 // keeps STAGES-1 chunks in flight without spending a warp — a 9th warp would put 3 warps on one SM
 // sub-partition and cap every thread at 168 registers (16K registers per sub-partition).
-template <int L, int NP, int STAGES> struct BkFromRing {
+// ORDER == 0: chunks are consumed in the order (c, r, half); ORDER == 1 (two-piece transforms, output-stationary
+// step): (c', c, r) — all digit polynomials against the two pieces of output component c' = 0, then c' = 1.
+template <int L, int NP, int STAGES, int ORDER = 0> struct BkFromRing {
     static constexpr int kChunksPerIter = 2 * L * NP;
     const double2* ring; uint64_t* full; uint64_t* empty;
     const double2* bk;        // start of the key, [n_iter][kChunksPerIter] chunks
@@ -73,7 +76,9 @@ template <int L, int NP, int STAGES> struct BkFromRing {
     // sequence number -> offset of the chunk in memory: consumption order is (c, r, half), storage (r, c, half)
     __device__ __forceinline__ size_t chunk_offset(int seq) const {
         int i = seq / kChunksPerIter, q = seq % kChunksPerIter;
-        int h = q % NP, cr = q / NP, r = cr % L, c = cr / L;
+        int h, cr;
+        if (ORDER == 0) { h = q % NP; cr = q / NP; } else { h = q / (2 * L); cr = q % (2 * L); }
+        int r = cr % L, c = cr / L;
         return ((size_t)i * kChunksPerIter + (size_t)((r * 2 + c) * NP + h)) * kChunkElems;
     }
     __device__ __forceinline__ void issue(int seq) {
@@ -211,6 +216,107 @@ __device__ __forceinline__ void extern_product_step_tmem(int32_t* acc, int abar,
     group_sync(bar_id);
 }
 
+// K2, output-stationary form for the two-piece (proven-exact) transform.
+//
+// extern_product_step_tmem keeps 2*NP = 4 output spectra alive while the 2L digit polynomials stream through
+// (64 accumulator registers + 64 TMEM columns that are read, updated and written back for every digit polynomial).
+// Here the loop nest is turned inside out:
+//
+//   phase 1   for q = (c, r):  rotate/subtract, digit r, forward transform  ->  F_q parked in TENSOR MEMORY
+//             (2L x 32 columns of this thread's TMEM row, written once)
+//   phase 2   for c' = 0, 1:   (lo, hi) = sum_q F_q * (BK[r][c][c'][piece 0], [piece 1])   one 16 KB ring chunk per q
+//                              inverse transform lo, hi; round; acc[c'] += lo + (hi << 16)
+//
+// so an output spectrum lives in registers from its first multiply-accumulate to its inverse transform, TMEM is
+// written once and read twice per F_q with no read-modify-write dependency (the load of F_{q+1} is in flight
+// behind the MAC of F_q), and the ~100 registers this frees hold all 15 twiddles of the thread (TwiddlesFull:
+// no twiddle is re-derived, 44 FP64 instructions less per transform).  With SYNC == 1 transforms the group meets at
+// one barrier per transform + one per iteration (9 instead of 19).
+//
+// X1 points at TWO consecutive 512-element buffers when SYNC == 1 (see fft512_forward_t).
+// The sums over q are taken in the same order as in every other kernel (c outer, r inner); in this mode all
+// results are exact integers anyway (exactness).
+__device__ __forceinline__ void tmem_ld_spectrum_raw(uint32_t taddr, int (&r0)[16], int (&r1)[16]) {
+    tmem_ld4_raw(taddr, r0);
+    tmem_ld4_raw(taddr + 16, r1);
+}
+// wait for the loads and pin the register reads behind the wait (an empty volatile asm that "modifies" them)
+__device__ __forceinline__ void tmem_ld_spectrum_finish(int (&r0)[16], int (&r1)[16], double2 (&v)[8]) {
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; i++) asm volatile("" : "+r"(r0[i]), "+r"(r1[i]));
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        v[i] = make_double2(__hiloint2double(r0[4 * i + 1], r0[4 * i]), __hiloint2double(r0[4 * i + 3], r0[4 * i + 2]));
+        v[4 + i] = make_double2(__hiloint2double(r1[4 * i + 1], r1[4 * i]), __hiloint2double(r1[4 * i + 3], r1[4 * i + 2]));
+    }
+}
+
+template <int L, int BGBIT, int SYNC, class BK, class W>
+__device__ __forceinline__ void extern_product_step_os(int32_t* acc, int abar, BK& bk, const W& w, double2* X1, double2* X2,
+                                                       uint32_t tm, int t, int bar_id) {
+    constexpr int Q = 2 * L;
+    constexpr uint32_t offset = decomp_offset<L, BGBIT>();
+    const int s = abar & 2047;
+    // ---- phase 1: the Q forward transforms ----
+#pragma unroll 1
+    for (int c = 0; c < 2; c++) {
+        const int32_t* p = acc + c * kN;
+        uint32_t tl[8], th[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            int j = t + 64 * m;
+            tl[m] = (uint32_t)rot_coeff(p, j, s) - (uint32_t)p[j] + offset;                 // bootstrap.jl:21
+            th[m] = (uint32_t)rot_coeff(p, j + 512, s) - (uint32_t)p[j + 512] + offset;
+        }
+#pragma unroll 1
+        for (int r = 0; r < L; r++) {
+            double2 a[8];
+#pragma unroll
+            for (int m = 0; m < 8; m++)
+                a[m] = make_double2(digit_f64<BGBIT>(tl[m], r), -digit_f64<BGBIT>(th[m], r));   // tgsw.jl:104-116
+            const int q = c * L + r;
+            fft512_forward_t<SYNC>(a, w, X1 + (SYNC ? (q & 1) * kSpectrum : 0), X2, t, bar_id, NoPrefetch());
+            tmem_store_spectrum(tm + (uint32_t)(q * 32), a);
+        }
+    }
+    tmem_wait_st();   // this thread's F_q have landed; every acc read of the group precedes the last transform's barrier
+    // ---- phase 2: one output component at a time ----
+#pragma unroll 1
+    for (int c2 = 0; c2 < 2; c2++) {
+        double2 lo[8], hi[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) { lo[e] = make_double2(0.0, 0.0); hi[e] = make_double2(0.0, 0.0); }
+        int r0[16], r1[16];
+        tmem_ld_spectrum_raw(tm, r0, r1);
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            double2 F[8];
+            tmem_ld_spectrum_finish(r0, r1, F);
+            if (q + 1 < Q) tmem_ld_spectrum_raw(tm + (uint32_t)((q + 1) * 32), r0, r1);   // in flight behind the MAC below
+            const double2* b = bk.acquire(0) + t;
+#pragma unroll
+            for (int e = 0; e < 8; e++) cmac(lo[e], F[e], BK::load(b + e * 64));             // tgsw.jl:128
+#pragma unroll
+            for (int e = 0; e < 8; e++) cmac(hi[e], F[e], BK::load(b + (8 + e) * 64));
+            bk.release();
+        }
+        uint32_t rl[8], rh[8];
+        fft512_inverse_t<SYNC>(lo, w, X1, X2, t, bar_id);
+#pragma unroll
+        for (int m = 0; m < 8; m++) { rl[m] = round_to_u32_fast<true>(lo[m].x); rh[m] = round_to_u32_fast<true>(-lo[m].y); }   // polynomials.jl:115-116
+        fft512_inverse_t<SYNC>(hi, w, X1 + (SYNC ? kSpectrum : 0), X2, t, bar_id);
+        int32_t* p = acc + c2 * kN;
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            const int j = t + 64 * m;
+            p[j] = (int32_t)((uint32_t)p[j] + rl[m] + (round_to_u32_fast<true>(hi[m].x) << 16));                           // bootstrap.jl:22
+            p[j + 512] = (int32_t)((uint32_t)p[j + 512] + rh[m] + (round_to_u32_fast<true>(-hi[m].y) << 16));
+        }
+    }
+    group_sync(bar_id);   // the updated accumulator is visible to the whole group before the next rotation reads it
+}
+
 // ---- K4T: key switch of a TILE of 64 ciphertexts per CTA (keyswitch.jl:45-80) ---------------------------------
 // keyswitch_kernel (one CTA per ciphertext) gathers 12.3 MB of table rows per ciphertext from L2 and runs at the
 // L2 bandwidth limit (13.9 TB/s).  Here a CTA owns 64 ciphertexts and streams the WHOLE table once through shared
@@ -329,14 +435,16 @@ struct BlindRotateArgs {
 
 // per-group shared memory: X1 + X2 + acc (+ bara, n_pad words)
 __host__ __device__ constexpr int group_smem_bytes(int /*NP*/) { return (kSpectrum + kX2Elems) * 16 + 2 * kN * 4; }
-__host__ __device__ constexpr size_t br_smem_bytes(int NP, int G, int STAGES, int n_pad) {
-    return (size_t)STAGES * kChunkBytes + 128 + (size_t)G * (group_smem_bytes(NP) + n_pad * 4);
+__host__ __device__ constexpr size_t br_smem_bytes(int NP, int G, int STAGES, int n_pad, int TM = 0) {
+    // TM == 3 (output-stationary step, SYNC == 1 transforms): a second X1 buffer per group
+    return (size_t)STAGES * kChunkBytes + 128 + (size_t)G * (group_smem_bytes(NP) + (TM == 3 ? kSpectrum * 16 : 0) + n_pad * 4);
 }
 
 // TMEM columns to allocate when the accumulators live in tensor memory: warps that share a lane quarter
 // (warp % 4) get disjoint column ranges of 64*NP columns each; allocations are powers of two.
-__host__ __device__ constexpr int br_tmem_cols(int NP, int G) {
-    int need = ((2 * G + 3) / 4) * 64 * NP, c = 32;
+__host__ __device__ constexpr int br_tmem_cols_per_warp(int NP, int L, int TM) { return TM == 3 ? 2 * L * 32 : 64 * NP; }
+__host__ __device__ constexpr int br_tmem_cols(int NP, int G, int L = 2, int TM = 1) {
+    int need = ((2 * G + 3) / 4) * br_tmem_cols_per_warp(NP, L, TM), c = 32;
     while (c < need) c *= 2;
     return c;
 }
@@ -345,9 +453,15 @@ template <int L, int BGBIT, int NP, int G, int STAGES, int MODE, int TM = 0>
 __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t s_tmem_base;
-    constexpr bool kUseTmem = TM != 0;   // TM: 0 = accumulators in registers, 1 = all in TMEM, 2 = component 1 in TMEM
+    // TM: 0 = accumulators in registers, 1 = all in TMEM, 2 = component 1 in TMEM,
+    //     3 = output-stationary step (extern_product_step_os; NP == 2): forward spectra in TMEM, full twiddle set
+    constexpr bool kUseTmem = TM != 0;
+    static_assert(TM != 3 || NP == 2, "the output-stationary step is the two-piece path");
+    constexpr int kTmemCols = br_tmem_cols(NP, G, L, TM);
+    static_assert(kTmemCols <= 512, "tensor memory: too many gates per CTA");
+    constexpr size_t kGroupBytes = group_smem_bytes(NP) + (TM == 3 ? kSpectrum * 16 : 0);
     if (kUseTmem) {
-        if ((threadIdx.x >> 5) == 0) tmem_alloc<br_tmem_cols(NP, G)>(&s_tmem_base);
+        if ((threadIdx.x >> 5) == 0) tmem_alloc<kTmemCols>(&s_tmem_base);
         tmem_fence_before_sync();
     }
     double2* ring = reinterpret_cast<double2*>(smem_raw);
@@ -364,22 +478,22 @@ __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs
     if (kUseTmem) {
         tmem_fence_after_sync();
         const int warp = threadIdx.x >> 5;
-        tm = s_tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 64 * NP);
+        tm = s_tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * br_tmem_cols_per_warp(NP, L, TM));
     }
-    BkFromRing<L, NP, STAGES> bk{ring, full, empty, A.bk_fft, A.n_iter * 2 * L * NP, 0, 0, 0u, threadIdx.x == 0};
+    BkFromRing<L, NP, STAGES, TM == 3 ? 1 : 0> bk{ring, full, empty, A.bk_fft, A.n_iter * 2 * L * NP, 0, 0, 0u, threadIdx.x == 0};
     bk.prologue();   // the first STAGES-1 chunks are in flight while the gate prologue below runs
 
     // ---------------- consumers: one 64-thread group per gate ----------------
     const int t = threadIdx.x & 63, grp = threadIdx.x >> 6;
     const int bar_id = grp + 1;
-    unsigned char* base = groups + (size_t)grp * (group_smem_bytes(NP) + A.n_pad * 4);
-    double2* X1 = reinterpret_cast<double2*>(base);
-    double2* X2 = X1 + kSpectrum;
+    unsigned char* base = groups + (size_t)grp * (kGroupBytes + A.n_pad * 4);
+    double2* X1 = reinterpret_cast<double2*>(base);                      // TM == 3: two buffers, used alternately
+    double2* X2 = X1 + (TM == 3 ? 2 : 1) * kSpectrum;
     int32_t* acc = reinterpret_cast<int32_t*>(X2 + kX2Elems);
     int32_t* bara = acc + 2 * kN;
     const unsigned long long g = (unsigned long long)blockIdx.x * G + grp;
     const bool valid = g < A.count;   // a group without a gate still walks the ring (on zeros) to keep the lockstep
-    Twiddles w; w.load(A.E, t);
+    typename std::conditional<TM == 3, TwiddlesFull, Twiddles>::type w; w.load(A.E, t);
 
     if (!valid) {
         for (int x = t; x < 2 * kN; x += 64) acc[x] = 0;
@@ -416,7 +530,8 @@ __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs
 
 #pragma unroll 1
     for (int i = 0; i < A.n_iter; i++) {   // bootstrap.jl:19-23
-        if (TM) extern_product_step_tmem<L, BGBIT, NP, (TM == 2 && NP == 2) ? 1 : 0>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id);
+        if constexpr (TM == 3) extern_product_step_os<L, BGBIT, 1>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id);
+        else if constexpr (TM != 0) extern_product_step_tmem<L, BGBIT, NP, (TM == 2 && NP == 2) ? 1 : 0>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id);
         else extern_product_step<L, BGBIT, NP, true, true>(acc, bara[i], bk, w, X1, X2, t, bar_id);
     }
 
@@ -433,7 +548,7 @@ __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs
     if (kUseTmem) {
         tmem_fence_before_sync();
         __syncthreads();
-        if ((threadIdx.x >> 5) == 0) tmem_dealloc<br_tmem_cols(NP, G)>(s_tmem_base);
+        if ((threadIdx.x >> 5) == 0) tmem_dealloc<kTmemCols>(s_tmem_base);
     }
 }
 

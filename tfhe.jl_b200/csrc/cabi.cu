@@ -113,7 +113,7 @@ int env_int(const char* name, int dflt) {
 template <int L, int BGBIT, int NP, int G, int STAGES, int MODE, int TM = 0>
 int launch_br_g(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
     auto kern = blind_rotate_kernel<L, BGBIT, NP, G, STAGES, MODE, TM>;
-    const size_t smem = br_smem_bytes(NP, G, STAGES, A.n_pad);
+    const size_t smem = br_smem_bytes(NP, G, STAGES, A.n_pad, TM);
     if (smem > 227 * 1024) return fail(ctx, TFHE_B200_EINVAL, "LWE dimension too large for the shared-memory layout");
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned grid = (unsigned)((A.count + G - 1) / G);
@@ -135,6 +135,9 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
             case 106: return launch_br_g<L, BGBIT, NP, 6, 3, MODE, 1>(ctx, A, s);
             case 204: return launch_br_g<L, BGBIT, NP, 4, 6, MODE, 2>(ctx, A, s);   // component 0 in registers, component 1 in TMEM
             case 4: return launch_br_g<L, BGBIT, NP, 4, 6, MODE>(ctx, A, s);           // register accumulators
+            case 304:                                                                   // output-stationary step (two pieces only)
+                if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3>(ctx, A, s);
+                else return launch_br_g<L, BGBIT, NP, 4, 6, MODE>(ctx, A, s);
             default:
                 // measured (profiles/r1): with one 32-bit piece the 64 accumulator registers fit and registers win
                 // (148 k vs 135 k gates/s); with two pieces (128 registers) the fastest is component 0 in registers

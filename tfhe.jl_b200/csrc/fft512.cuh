@@ -106,23 +106,63 @@ struct Twiddles {
     }
 };
 
+// All 15 twiddles of a thread, read once from the table (every entry correctly rounded from long double) instead of
+// being re-derived by 11 complex multiplications in every transform: 44 fewer FP64 instructions per transform and
+// thread for 32 more registers.  Used by the kernels whose register budget allows it (blind_rotate.cuh, TM == 3).
+struct TwiddlesFull {
+    double2 T[8];   // T[q]  = E(t*(4q+1))   pass-1 twiddle merged with the per-thread part of the twist
+    double2 V[8];   // V[q2] = E(32*t1*q2) = W64^(t1*q2), t1 = t & 7;  V[0] = 1 is never used
+    __device__ __forceinline__ void load(const double2* __restrict__ E, int t) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) T[q] = E[t * (4 * q + 1)];          // <= 63*29 = 1827 < 2048
+        const int t1 = t & 7;
+        V[0] = make_double2(1.0, 0.0);
+#pragma unroll
+        for (int q2 = 1; q2 < 8; q2++) V[q2] = E[32 * t1 * q2];         // <= 32*49 = 1568
+    }
+};
+
+__device__ __forceinline__ void pass1_twiddles(const Twiddles& w, double2 (&T)[8]) {
+    T[0] = w.e1; T[1] = cmul(w.e1, w.s1); T[2] = cmul(w.e1, w.s2); T[3] = cmul(T[1], w.s2); T[4] = cmul(w.e1, w.s4);
+    T[5] = cmul(T[1], w.s4); T[6] = cmul(T[2], w.s4); T[7] = cmul(T[3], w.s4);
+}
+__device__ __forceinline__ void pass1_twiddles(const TwiddlesFull& w, double2 (&T)[8]) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) T[q] = w.T[q];
+}
+__device__ __forceinline__ void pass2_twiddles(const Twiddles& w, double2 (&V)[8]) {
+    V[1] = w.v1; V[2] = w.v2; V[3] = cmul(w.v1, w.v2); V[4] = w.v4; V[5] = cmul(w.v1, w.v4); V[6] = cmul(w.v2, w.v4);
+    V[7] = cmul(V[3], w.v4);
+}
+__device__ __forceinline__ void pass2_twiddles(const TwiddlesFull& w, double2 (&V)[8]) {
+#pragma unroll
+    for (int q = 1; q < 8; q++) V[q] = w.V[q];
+}
+
 // Forward transform.  In: a[m] = z_{t+64m} (untwisted).  Out: a[q3] = Z_{q + 8*q2 + 64*q3}, v = q2 + 8q = t.
 // X1, X2: two 512-element double2 scratch buffers private to the 64-thread group.
 struct NoPrefetch { __device__ __forceinline__ void operator()() const {} };
 
 // `prefetch` runs right after the second barrier, before the X2 loads are issued: callers use it to put
 // further shared-memory loads (the key chunk of the multiply-accumulate) in flight behind the same wait.
-template <class F = NoPrefetch>
-__device__ __forceinline__ void fft512_forward(double2 (&a)[8], const Twiddles& w, double2* X1, double2* X2, int t,
-                                               int bar_id, F&& prefetch = F()) {
+// SYNC == 0: both exchanges are fenced by the 64-thread group barrier; X1 may be the same buffer in every call.
+// SYNC == 1: the second exchange stays inside 8-thread tiles (threads 8*hi .. 8*hi+7, all in one warp), so it only
+//            needs __syncwarp(); the one group barrier left per transform sits between the X1 stores and loads.
+//            The caller must then ALTERNATE between two X1 buffers from one transform to the next (a warp that has
+//            passed the barrier of transform k may already store pass-1 results of transform k+1 while the other warp
+//            of the group still loads X1 of transform k; it cannot reach transform k+2 before that warp has arrived at
+//            the barrier of transform k+1, i.e. has consumed those loads).
+template <int SYNC, class W, class F>
+__device__ __forceinline__ void fft512_forward_t(double2 (&a)[8], const W& w, double2* X1, double2* X2, int t,
+                                                 int bar_id, F&& prefetch) {
 #pragma unroll
     for (int m = 1; m < 8; m++) a[m] = cmul(a[m], make_double2(kTwistRe[m], kTwistIm[m]));
     dft8<false>(a);
     {
-        double2 T1 = cmul(w.e1, w.s1), T2 = cmul(w.e1, w.s2), T3 = cmul(T1, w.s2), T4 = cmul(w.e1, w.s4);
-        double2 T5 = cmul(T1, w.s4), T6 = cmul(T2, w.s4), T7 = cmul(T3, w.s4);
-        a[0] = cmul(a[0], w.e1); a[1] = cmul(a[1], T1); a[2] = cmul(a[2], T2); a[3] = cmul(a[3], T3);
-        a[4] = cmul(a[4], T4); a[5] = cmul(a[5], T5); a[6] = cmul(a[6], T6); a[7] = cmul(a[7], T7);
+        double2 T[8];
+        pass1_twiddles(w, T);
+#pragma unroll
+        for (int q = 0; q < 8; q++) a[q] = cmul(a[q], T[q]);
     }
 #pragma unroll
     for (int q = 0; q < 8; q++) X1[q * 64 + t] = a[q];
@@ -132,33 +172,42 @@ __device__ __forceinline__ void fft512_forward(double2 (&a)[8], const Twiddles& 
     for (int t2 = 0; t2 < 8; t2++) a[t2] = X1[hi * 64 + lo + 8 * t2];
     dft8<false>(a);
     {
-        double2 v3 = cmul(w.v1, w.v2), v5 = cmul(w.v1, w.v4), v6 = cmul(w.v2, w.v4), v7 = cmul(v3, w.v4);
-        a[1] = cmul(a[1], w.v1); a[2] = cmul(a[2], w.v2); a[3] = cmul(a[3], v3); a[4] = cmul(a[4], w.v4);
-        a[5] = cmul(a[5], v5); a[6] = cmul(a[6], v6); a[7] = cmul(a[7], v7);
+        double2 V[8];
+        pass2_twiddles(w, V);
+#pragma unroll
+        for (int q = 1; q < 8; q++) a[q] = cmul(a[q], V[q]);
     }
+    if (SYNC == 1) __syncwarp();   // the tile's loads of the previous transform's X2 are done
 #pragma unroll
     for (int q2 = 0; q2 < 8; q2++) X2[hi * 72 + q2 * 9 + lo] = a[q2];
-    group_sync(bar_id);
+    if (SYNC == 1) __syncwarp(); else group_sync(bar_id);
     prefetch();
 #pragma unroll
     for (int t1 = 0; t1 < 8; t1++) a[t1] = X2[hi * 72 + lo * 9 + t1];
     dft8<false>(a);
 }
+template <class W, class F = NoPrefetch>
+__device__ __forceinline__ void fft512_forward(double2 (&a)[8], const W& w, double2* X1, double2* X2, int t, int bar_id,
+                                               F&& prefetch = F()) {
+    fft512_forward_t<0>(a, w, X1, X2, t, bar_id, prefetch);
+}
 
 // Inverse transform, the mirror of fft512_forward.  In: a[q3] spectrum at thread v.  Out: a[m] = z_{t+64m}
 // scaled by 1/512 and untwisted, i.e. the folded coefficients (p_j - i*p_{j+512}).
-__device__ __forceinline__ void fft512_inverse(double2 (&a)[8], const Twiddles& w, double2* X1, double2* X2, int t,
-                                               int bar_id) {
+template <int SYNC, class W>
+__device__ __forceinline__ void fft512_inverse_t(double2 (&a)[8], const W& w, double2* X1, double2* X2, int t, int bar_id) {
     const int lo = t & 7, hi = t >> 3;
     dft8<true>(a);   // q3 -> t1
     {
-        double2 v3 = cmul(w.v1, w.v2), v5 = cmul(w.v1, w.v4), v6 = cmul(w.v2, w.v4), v7 = cmul(v3, w.v4);
-        a[1] = cmulc(a[1], w.v1); a[2] = cmulc(a[2], w.v2); a[3] = cmulc(a[3], v3); a[4] = cmulc(a[4], w.v4);
-        a[5] = cmulc(a[5], v5); a[6] = cmulc(a[6], v6); a[7] = cmulc(a[7], v7);
+        double2 V[8];
+        pass2_twiddles(w, V);
+#pragma unroll
+        for (int q = 1; q < 8; q++) a[q] = cmulc(a[q], V[q]);
     }
+    if (SYNC == 1) __syncwarp();
 #pragma unroll
     for (int t1 = 0; t1 < 8; t1++) X2[hi * 72 + lo * 9 + t1] = a[t1];
-    group_sync(bar_id);
+    if (SYNC == 1) __syncwarp(); else group_sync(bar_id);
 #pragma unroll
     for (int q2 = 0; q2 < 8; q2++) a[q2] = X2[hi * 72 + q2 * 9 + lo];
     dft8<true>(a);   // q2 -> t2
@@ -168,16 +217,20 @@ __device__ __forceinline__ void fft512_inverse(double2 (&a)[8], const Twiddles& 
 #pragma unroll
     for (int q = 0; q < 8; q++) a[q] = X1[q * 64 + t];
     {
-        double2 T1 = cmul(w.e1, w.s1), T2 = cmul(w.e1, w.s2), T3 = cmul(T1, w.s2), T4 = cmul(w.e1, w.s4);
-        double2 T5 = cmul(T1, w.s4), T6 = cmul(T2, w.s4), T7 = cmul(T3, w.s4);
-        a[0] = cmulc(a[0], w.e1); a[1] = cmulc(a[1], T1); a[2] = cmulc(a[2], T2); a[3] = cmulc(a[3], T3);
-        a[4] = cmulc(a[4], T4); a[5] = cmulc(a[5], T5); a[6] = cmulc(a[6], T6); a[7] = cmulc(a[7], T7);
+        double2 T[8];
+        pass1_twiddles(w, T);
+#pragma unroll
+        for (int q = 0; q < 8; q++) a[q] = cmulc(a[q], T[q]);
     }
     dft8<true>(a);   // q -> m
     constexpr double sc = 1.0 / 512.0;
     a[0] = make_double2(a[0].x * sc, a[0].y * sc);
 #pragma unroll
     for (int m = 1; m < 8; m++) a[m] = cmulc(a[m], make_double2(kTwistRe[m] * sc, kTwistIm[m] * sc));
+}
+template <class W>
+__device__ __forceinline__ void fft512_inverse(double2 (&a)[8], const W& w, double2* X1, double2* X2, int t, int bar_id) {
+    fft512_inverse_t<0>(a, w, X1, X2, t, bar_id);
 }
 
 // round-to-nearest-even to a 64-bit integer, keep the low 32 bits (polynomials.jl:115-116)

@@ -1,4 +1,10 @@
-"""MK-TFHE NAND throughput probe (BASELINE.json config #5): parties in {2,4,8}, device-resident inputs."""
+"""MK-TFHE NAND throughput probe (BASELINE.json config #5): parties in {2,4,8}, device-resident inputs.
+
+Parity is judged on CIPHERTEXT equality with the oracle on a sample of the batch that includes every gate whose
+decryption differs from NAND (`oracle_identical`).  `decrypts_to_nand` is informational: the reference's own MK
+output noise (sigma ~ 0.05 for 2 parties) makes an occasional full-size gate decrypt wrongly in the reference too;
+when that happens here, `oracle_decrypts_the_same` says whether the oracle's ciphertext decrypts to the same bit.
+"""
 import os, sys, json, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -8,6 +14,7 @@ from oracle import oracle as O
 def main():
     p = int(sys.argv[1]); B = int(sys.argv[2]); n = int(sys.argv[3]) if len(sys.argv) > 3 else 500
     flags = int(os.environ.get("FLAGS", "0"))
+    nsample = int(os.environ.get("SAMPLE", "16"))
     P = O.small_params(O.MK_PARAMS[p], n)
     t0 = time.time(); mk = O.mk_keygen(P, p, 5); t_keygen = time.time() - t0
     ctx = T.Context(n=P.n, l=P.l, bgbit=P.bgbit, t=P.t, basebit=P.basebit, parties=p, flags=flags)
@@ -15,7 +22,9 @@ def main():
     base = min(B, 64)
     bits = np.random.default_rng(0).integers(0, 2, (base, 2)).astype(bool)
     rng = O.Rng(1)
-    x = np.tile(O.mk_encrypt(rng, mk, bits[:, 0]), (B // base, 1)); y = np.tile(O.mk_encrypt(rng, mk, bits[:, 1]), (B // base, 1))
+    xb, yb = O.mk_encrypt(rng, mk, bits[:, 0]), O.mk_encrypt(rng, mk, bits[:, 1])
+    reps = (B + base - 1) // base
+    x = np.tile(xb, (reps, 1))[:B]; y = np.tile(yb, (reps, 1))[:B]
     dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(); out = torch.empty_like(dx)
     s = torch.cuda.current_stream().cuda_stream
     fn = lambda: ctx.mk_nand_dev(dx.data_ptr(), dy.data_ptr(), out.data_ptr(), B, stream=s)
@@ -23,7 +32,19 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); fn(); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    dec = O.mk_decrypt(mk, out.cpu().numpy()[:base])
+    got = out.cpu().numpy()
+    want_bits = np.tile(~(bits[:, 0] & bits[:, 1]), reps)[:B]
+    dec = O.mk_decrypt(mk, got)
+    wrong = np.flatnonzero(dec != want_bits)
+    # the batch repeats `base` distinct gates: every repetition must be the same ciphertext
+    self_consistent = bool(np.array_equal(got, np.tile(got[:base], (reps, 1))[:B]))
+    sample = np.unique(np.r_[np.arange(min(nsample, base)), wrong % base])
+    octx = O.MKContext(mk)
+    want = octx.nand(xb[sample], yb[sample])
+    identical = bool(np.array_equal(got[sample], want))
+    odec = O.mk_decrypt(mk, want)
     print(json.dumps({"parties": p, "n": n, "B": B, "flags": flags, "ms": ms, "gates_per_s": B / ms * 1e3,
-                      "correct": bool(np.array_equal(dec, ~(bits[:, 0] & bits[:, 1]))), "oracle_keygen_s": t_keygen}))
+                      "oracle_identical": identical, "oracle_sample": int(sample.size), "batch_self_consistent": self_consistent,
+                      "decrypts_to_nand": int(B - wrong.size), "wrong_decryptions": int(wrong.size),
+                      "oracle_decrypts_the_same": bool(np.array_equal(odec, dec[sample])), "oracle_keygen_s": t_keygen}))
 main()
