@@ -23,7 +23,8 @@
  *     the results do not depend on the choice.
  *   - there is NO CPU fallback: without a CUDA device every call fails with TFHE_B200_ENODEV.
  *   - calls on one context are serialised by an internal mutex; contexts are independent
- *     (one context per GPU; gate batches shard across contexts with no collective).
+ *     (one context per GPU; gate batches shard across contexts with no collective: tfhe_b200_multi_* below).
+ *   - error texts are kept per calling thread (errno style).
  *
  * Layouts
  *   LWE ciphertext batch     [count][n+1]            a[0..n-1], b   (lwe.jl:21-29); this is the
@@ -149,6 +150,10 @@ int tfhe_b200_mk_load_ksk(tfhe_b200_ctx* ctx, const int32_t* mk_ksk);
 int tfhe_b200_mk_nand_batch(tfhe_b200_ctx* ctx, const int32_t* x, const int32_t* y, int32_t* out, size_t count);
 int tfhe_b200_mk_nand_batch_dev(tfhe_b200_ctx* ctx, const int32_t* x, const int32_t* y, int32_t* out, size_t count,
                                 void* stream);
+/* mk_bootstrap (mk_internals.jl:512-515): mk_keyswitch(ks, mk_bootstrap_wo_keyswitch(bk, mu, x)), [count][p*n+1] in and out */
+int tfhe_b200_mk_bootstrap_batch(tfhe_b200_ctx* ctx, int32_t mu, const int32_t* x, int32_t* out, size_t count);
+int tfhe_b200_mk_bootstrap_batch_dev(tfhe_b200_ctx* ctx, int32_t mu, const int32_t* x, int32_t* out, size_t count,
+                                     void* stream);
 /* mk_bootstrap_wo_keyswitch (mk_internals.jl:498-509): out [count][p*N+1] */
 int tfhe_b200_mk_bootstrap_wo_ks_batch(tfhe_b200_ctx* ctx, int32_t mu, const int32_t* x, int32_t* out, size_t count);
 /* mk_keyswitch (mk_internals.jl:397-411): in [count][p*N+1] -> out [count][p*n+1] */
@@ -156,6 +161,34 @@ int tfhe_b200_mk_keyswitch_batch(tfhe_b200_ctx* ctx, const int32_t* in, int32_t*
 /* mk_tgsw_extern_mul (mk_internals.jl:348-391): out[g] = BK[party[g]][bk_index[g]] (x) acc[g]; acc/out [count][p+1][N] */
 int tfhe_b200_mk_extern_product_batch(tfhe_b200_ctx* ctx, const int32_t* acc, const int32_t* party,
                                       const int32_t* bk_index, int32_t* out, size_t count);
+
+/* ---- one logical context over several GPUs ------------------------------------ */
+/* Gates are independent (gates.jl:15-18) and the evaluation keys are read-only, so a batch shards across GPUs with
+ * no exchange step: keys are replicated at load, every call cuts its batch into contiguous shards of whole CTA
+ * waves, one host thread per device runs its shard through the single-device entry point above and writes a
+ * disjoint slice of the caller's output.  device_ids == NULL or n_dev <= 0 selects every visible device.
+ * This is what a Julia `CloudKey(...; devices = ...)` holds so that ONE gate_nand.(ck, xs, ys) uses every GPU. */
+typedef struct tfhe_b200_multi tfhe_b200_multi;
+int tfhe_b200_multi_create(const tfhe_b200_params* params, const int* device_ids, int n_dev, uint32_t flags,
+                           tfhe_b200_multi** out);
+void tfhe_b200_multi_destroy(tfhe_b200_multi* m);
+/* last error of a tfhe_b200_multi_* call on the calling thread (m may be NULL) */
+const char* tfhe_b200_multi_last_error(const tfhe_b200_multi* m);
+int tfhe_b200_multi_devices(const tfhe_b200_multi* m);
+/* the single-device context of the i-th listed device (for the *_dev entry points); owned by m */
+tfhe_b200_ctx* tfhe_b200_multi_context(tfhe_b200_multi* m, int i);
+uint64_t tfhe_b200_multi_kernel_launches(const tfhe_b200_multi* m);
+/* key replication: same layouts as the single-device loaders, one host thread per device */
+int tfhe_b200_multi_load_bk(tfhe_b200_multi* m, const int32_t* bk);
+int tfhe_b200_multi_load_ksk(tfhe_b200_multi* m, const int32_t* ksk);
+int tfhe_b200_multi_mk_load_bk(tfhe_b200_multi* m, const int32_t* mk_bk);
+int tfhe_b200_multi_mk_load_ksk(tfhe_b200_multi* m, const int32_t* mk_ksk);
+/* gate_* (gates.jl:15-177), bootstrap (bootstrap.jl:92-95) / mk_bootstrap (mk_internals.jl:512-515) and
+ * mk_gate_nand (mk_gates.jl:7-12) over a batch in host memory, sharded over the devices */
+int tfhe_b200_multi_gate_batch(tfhe_b200_multi* m, int op, const int32_t* x, const int32_t* y, const int32_t* z,
+                               int32_t* out, size_t count);
+int tfhe_b200_multi_bootstrap_batch(tfhe_b200_multi* m, int32_t mu, const int32_t* x, int32_t* out, size_t count);
+int tfhe_b200_multi_mk_nand_batch(tfhe_b200_multi* m, const int32_t* x, const int32_t* y, int32_t* out, size_t count);
 
 #ifdef __cplusplus
 }

@@ -285,3 +285,59 @@ def test_tiled_keyswitch_equals_per_ciphertext_kernel(keys80, gctx80, monkeypatc
     assert np.array_equal(got, ctx.keyswitch(u))
     octx = O.Context(keys80)
     assert np.array_equal(got[:8], octx.keyswitch(u[:8]))
+
+
+def test_multi_device_context_shards_equal_single_device(keys80_small, octx80_small):
+    """tfhe_b200_multi_*: the batch is cut into contiguous shards, one host thread per GPU, disjoint output slices.
+    With one GPU the code path (threads, sharding, replicated key load) is the same; with two or more the result must
+    still equal the single-device ciphertexts bit for bit."""
+    ndev = T.device_count()
+    P = keys80_small.params
+    kw = dict(n=P.n, l=P.l, bgbit=P.bgbit, t=P.t, basebit=P.basebit)
+    single = T.Context(**kw)
+    single.load_bk(keys80_small.bk); single.load_ksk(keys80_small.ksk)
+    count = 1201
+    bits = np.random.default_rng(9).integers(0, 2, (count, 3)).astype(bool)
+    rng = O.Rng(9)
+    x, y, z = (O.encrypt(rng, keys80_small, bits[:, i]) for i in range(3))
+    want_nand, want_mux = single.gate(O.NAND, x, y), single.gate(O.MUX, x, y, z)
+    assert np.array_equal(want_nand[:64], octx80_small.gate(O.NAND, x[:64], y[:64]))
+    for devs in ([0], list(range(ndev)) if ndev > 1 else None):
+        if devs is None and ndev == 1:
+            devs = None   # "all visible devices"
+        m = _cabi.MultiContext(devices=devs, **kw)
+        assert m.devices == (len(devs) if devs else ndev)
+        m.load_bk(keys80_small.bk); m.load_ksk(keys80_small.ksk)
+        assert np.array_equal(m.gate(O.NAND, x, y), want_nand)
+        assert np.array_equal(m.gate(O.MUX, x, y, z), want_mux)
+        assert np.array_equal(m.gate(O.NAND, x[:3], y[:3]), want_nand[:3])      # fewer gates than devices x waves
+        assert np.array_equal(m.bootstrap(x[:70]), single.bootstrap(x[:70]))
+        assert m.kernel_launches > 0
+        m.close()
+    with pytest.raises(T.TFHEB200Error):
+        _cabi.MultiContext(devices=[0, 0], **kw)
+    with pytest.raises(T.TFHEB200Error):
+        _cabi.MultiContext(devices=[ndev], **kw)
+
+
+def test_cloud_key_over_all_devices_matches_reference_usage():
+    """docs/src/manual.md:28-35 usage with CloudKey(devices="all"): one gate call, every GPU."""
+    rng = np.random.default_rng(11)
+    sk, ck = T.make_key_pair(rng, devices="all")
+    bits = rng.integers(0, 2, (2, 700)).astype(bool)
+    x, y = T.encrypt(rng, sk, bits[0]), T.encrypt(rng, sk, bits[1])
+    assert np.array_equal(T.decrypt(sk, T.gate_xor(ck, x, y)), bits[0] ^ bits[1])
+    assert ck.mctx.devices == T.device_count()
+
+
+def test_pageable_and_unaligned_host_buffers(keys80, gctx80):
+    """The C ABI accepts plain pageable host memory (a Julia Matrix{Int32}); a batch large enough for the chunked,
+    double-buffered copy pipeline (4 chunks) must give the same ciphertexts as the device-resident path."""
+    count = 8 * 4 * 148 + 5
+    rng = O.Rng(12)
+    bits = np.random.default_rng(12).integers(0, 2, (64, 2)).astype(bool)
+    x = np.tile(O.encrypt(rng, keys80, bits[:, 0]), (count // 64 + 1, 1))[:count]
+    y = np.tile(O.encrypt(rng, keys80, bits[:, 1]), (count // 64 + 1, 1))[:count]
+    out = gctx80.gate(O.AND, x, y)
+    assert np.array_equal(out, np.tile(out[:64], (count // 64 + 1, 1))[:count])
+    assert np.array_equal(out[:8], O.Context(keys80).gate(O.AND, x[:8], y[:8]))

@@ -80,6 +80,21 @@ def lib():
             "tfhe_b200_mk_bootstrap_wo_ks_batch": (C.c_int, [vp, C.c_int32, i32p, i32p, sz]),
             "tfhe_b200_mk_keyswitch_batch": (C.c_int, [vp, i32p, i32p, sz]),
             "tfhe_b200_mk_extern_product_batch": (C.c_int, [vp, i32p, i32p, i32p, i32p, sz]),
+            "tfhe_b200_mk_bootstrap_batch": (C.c_int, [vp, C.c_int32, i32p, i32p, sz]),
+            "tfhe_b200_mk_bootstrap_batch_dev": (C.c_int, [vp, C.c_int32, i32p, i32p, sz, vp]),
+            "tfhe_b200_multi_create": (C.c_int, [C.POINTER(CParams), C.POINTER(C.c_int), C.c_int, C.c_uint32, C.POINTER(vp)]),
+            "tfhe_b200_multi_destroy": (None, [vp]),
+            "tfhe_b200_multi_last_error": (C.c_char_p, [vp]),
+            "tfhe_b200_multi_devices": (C.c_int, [vp]),
+            "tfhe_b200_multi_context": (vp, [vp, C.c_int]),
+            "tfhe_b200_multi_kernel_launches": (C.c_uint64, [vp]),
+            "tfhe_b200_multi_load_bk": (C.c_int, [vp, i32p]),
+            "tfhe_b200_multi_load_ksk": (C.c_int, [vp, i32p]),
+            "tfhe_b200_multi_mk_load_bk": (C.c_int, [vp, i32p]),
+            "tfhe_b200_multi_mk_load_ksk": (C.c_int, [vp, i32p]),
+            "tfhe_b200_multi_gate_batch": (C.c_int, [vp, C.c_int, i32p, i32p, i32p, i32p, sz]),
+            "tfhe_b200_multi_bootstrap_batch": (C.c_int, [vp, C.c_int32, i32p, i32p, sz]),
+            "tfhe_b200_multi_mk_nand_batch": (C.c_int, [vp, i32p, i32p, i32p, sz]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -112,9 +127,20 @@ class Context:
         if rc != 0:
             raise TFHEB200Error(rc, (lib().tfhe_b200_last_error(None) or b"").decode())
 
+    @classmethod
+    def _borrowed(cls, handle, owner, n, N, k, l, bgbit, t, basebit, parties, device, flags):
+        """A view of a context owned by `owner` (a MultiContext): never destroyed from here."""
+        self = cls.__new__(cls)
+        self.n, self.N, self.k, self.l, self.bgbit, self.t, self.basebit, self.parties = n, N, k, l, bgbit, t, basebit, parties
+        self.device, self.flags = device, flags
+        self._h = C.c_void_p(handle)
+        self._owner = owner
+        return self
+
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
-            lib().tfhe_b200_destroy(self._h)
+            if getattr(self, "_owner", None) is None:
+                lib().tfhe_b200_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -189,6 +215,12 @@ class Context:
         self._ck(fn(self._h, mu, _addr(x), _addr(out), x.shape[0]))
         return out
 
+    def mk_bootstrap(self, x, mu=1 << 29):
+        x = np.atleast_2d(_host(x)); out = np.empty_like(x)
+        assert self.parties > 1 and x.shape[1] == self.ct_words
+        self._ck(lib().tfhe_b200_mk_bootstrap_batch(self._h, mu, _addr(x), _addr(out), x.shape[0]))
+        return out
+
     def keyswitch(self, u):
         u = np.atleast_2d(_host(u)); out = np.empty((u.shape[0], self.ct_words), dtype=np.int32)
         fn = lib().tfhe_b200_keyswitch_batch if self.parties == 1 else lib().tfhe_b200_mk_keyswitch_batch
@@ -239,6 +271,82 @@ class Context:
 
     def mk_nand_dev(self, x_ptr, y_ptr, out_ptr, count, stream=0):
         self._ck(lib().tfhe_b200_mk_nand_batch_dev(self._h, x_ptr, y_ptr, out_ptr, count, stream or None))
+
+
+class MultiContext:
+    """One logical evaluation context over several GPUs (tfhe_b200_multi_*): keys replicated at load, every batch cut
+    into contiguous shards, one host thread per device, disjoint slices of the output.  ``devices=None`` = all."""
+
+    def __init__(self, n, N=1024, k=1, l=2, bgbit=10, t=8, basebit=2, parties=1, devices=None, flags=FLAG_SPLIT_FFT):
+        self.n, self.N, self.k, self.l, self.bgbit, self.t, self.basebit, self.parties = n, N, k, l, bgbit, t, basebit, parties
+        self.flags = flags
+        self._h = C.c_void_p()
+        cp = CParams(n, N, k, l, bgbit, t, basebit, parties)
+        ids = None if devices is None else (C.c_int * len(devices))(*devices)
+        rc = lib().tfhe_b200_multi_create(C.byref(cp), ids, 0 if devices is None else len(devices), flags, C.byref(self._h))
+        if rc != 0:
+            raise TFHEB200Error(rc, (lib().tfhe_b200_multi_last_error(None) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().tfhe_b200_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise TFHEB200Error(rc, (lib().tfhe_b200_multi_last_error(self._h) or b"").decode())
+
+    @property
+    def devices(self) -> int:
+        return int(lib().tfhe_b200_multi_devices(self._h))
+
+    def context(self, i: int = 0) -> "Context":
+        """The single-device context of the i-th listed device (device-resident / *_dev entry points)."""
+        h = lib().tfhe_b200_multi_context(self._h, i)
+        if not h:
+            raise IndexError(i)
+        return Context._borrowed(h, self, self.n, self.N, self.k, self.l, self.bgbit, self.t, self.basebit, self.parties, i, self.flags)
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(lib().tfhe_b200_multi_kernel_launches(self._h))
+
+    @property
+    def ct_words(self):
+        return self.parties * self.n + 1
+
+    def load_bk(self, bk):
+        bk = _host(bk)
+        self._ck((lib().tfhe_b200_multi_load_bk if self.parties == 1 else lib().tfhe_b200_multi_mk_load_bk)(self._h, _addr(bk)))
+
+    def load_ksk(self, ksk):
+        ksk = _host(ksk)
+        self._ck((lib().tfhe_b200_multi_load_ksk if self.parties == 1 else lib().tfhe_b200_multi_mk_load_ksk)(self._h, _addr(ksk)))
+
+    def gate(self, op, x=None, y=None, z=None, count=None, out=None):
+        arrs = [None if a is None else np.atleast_2d(_host(a)) for a in (x, y, z)]
+        if count is None:
+            count = next(a.shape[0] for a in arrs if a is not None)
+        if out is None:
+            out = np.empty((count, self.ct_words), dtype=np.int32)
+        self._ck(lib().tfhe_b200_multi_gate_batch(self._h, op, _addr(arrs[0]), _addr(arrs[1]), _addr(arrs[2]), _addr(out), count))
+        return out
+
+    def bootstrap(self, x, mu=1 << 29):
+        x = np.atleast_2d(_host(x)); out = np.empty_like(x)
+        self._ck(lib().tfhe_b200_multi_bootstrap_batch(self._h, mu, _addr(x), _addr(out), x.shape[0]))
+        return out
+
+    def mk_nand(self, x, y):
+        x = np.atleast_2d(_host(x)); y = np.atleast_2d(_host(y)); out = np.empty_like(x)
+        self._ck(lib().tfhe_b200_multi_mk_nand_batch(self._h, _addr(x), _addr(y), _addr(out), x.shape[0]))
+        return out
 
 
 def device_count() -> int:

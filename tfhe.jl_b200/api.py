@@ -198,25 +198,36 @@ class CloudKey:                               # api.jl:111-127
     """Evaluation key.  Key material is generated on the host and loaded onto `device`; the int32
     coefficient form of the bootstrap key is kept (the reference keeps only its transform)."""
 
-    def __init__(self, rng, secret_key: SecretKey, device: int = 0, flags: int = _cabi.FLAG_SPLIT_FFT):
+    def __init__(self, rng, secret_key: SecretKey, device: int = 0, flags: int = _cabi.FLAG_SPLIT_FFT, devices=None):
+        """``devices``: a list of GPU ordinals or ``"all"`` — the key is then replicated on every listed GPU and each
+        gate batch is sharded across them (one ``gate_nand(ck, x, y)`` uses every GPU)."""
         p = secret_key.params
         self.params = p
-        self.ctx = _context(p, 1, device, flags)
+        self.mctx = None
+        if devices is not None:
+            self.mctx = _cabi.MultiContext(n=p.lwe_size, N=p.tlwe_polynomial_degree, k=p.tlwe_mask_size, l=p.bs_decomp_length,
+                                           bgbit=p.bs_log2_base, t=p.ks_decomp_length, basebit=p.ks_log2_base, parties=1,
+                                           devices=None if devices == "all" else list(devices), flags=flags)
+            self.ctx = self.mctx.context(0)
+        else:
+            self.ctx = _context(p, 1, device, flags)
         tlwe_key = rand_uniform_bool(rng, p.tlwe_mask_size, p.tlwe_polynomial_degree)     # TLweKey, tlwe.jl:15-20
         self.bootstrap_key = _bootstrap_key(rng, self.ctx, p.bs_noise_stddev, secret_key.key, tlwe_key,
                                             p.bs_decomp_length, p.bs_log2_base)
         self.keyswitch_key = _keyswitch_key(rng, p.ks_noise_stddev, p.ks_decomp_length, p.ks_log2_base, secret_key.key,
                                             tlwe_key.reshape(-1))                         # extract_lwe_key, tlwe.jl:25-31
-        self.ctx.load_bk(self.bootstrap_key)
-        self.ctx.load_ksk(self.keyswitch_key)
+        holder = self.mctx if self.mctx is not None else self.ctx
+        holder.load_bk(self.bootstrap_key)
+        holder.load_ksk(self.keyswitch_key)
 
 
-def make_key_pair(rng, params: Optional[SchemeParameters] = None, device: int = 0, flags: int = _cabi.FLAG_SPLIT_FFT):
+def make_key_pair(rng, params: Optional[SchemeParameters] = None, device: int = 0, flags: int = _cabi.FLAG_SPLIT_FFT,
+                  devices=None):
     """api.jl:139-146"""
     if params is None:
         params = tfhe_parameters_80()
     secret_key = SecretKey(rng, params)
-    return secret_key, CloudKey(rng, secret_key, device=device, flags=flags)
+    return secret_key, CloudKey(rng, secret_key, device=device, flags=flags, devices=devices)
 
 
 def encrypt(rng, key: SecretKey, message) -> LweSample:
@@ -235,7 +246,7 @@ def decrypt(key: SecretKey, sample: LweSample):
 # ------------------------------------------------------------------ gates.jl
 def _gate(ck: CloudKey, op: int, *xs: LweSample) -> LweSample:
     single = xs[0].data.ndim == 1
-    out = ck.ctx.gate(op, *[np.atleast_2d(x.data) for x in xs])
+    out = (ck.mctx if getattr(ck, "mctx", None) is not None else ck.ctx).gate(op, *[np.atleast_2d(x.data) for x in xs])
     return LweSample(out[0] if single else out, 0.0)
 
 
@@ -485,6 +496,7 @@ def load_cloud_key(path, device: int = 0, flags: int = _cabi.FLAG_SPLIT_FFT) -> 
         ck.params = _params_from(z["params"])
         ck.bootstrap_key = np.ascontiguousarray(z["bootstrap_key"], dtype=np.int32)
         ck.keyswitch_key = np.ascontiguousarray(z["keyswitch_key"], dtype=np.int32)
+    ck.mctx = None
     ck.ctx = _context(ck.params, 1, device, flags)
     ck.ctx.load_bk(ck.bootstrap_key)
     ck.ctx.load_ksk(ck.keyswitch_key)

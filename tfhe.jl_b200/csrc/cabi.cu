@@ -61,15 +61,16 @@ struct tfhe_b200_ctx {
     cudaStream_t scratch_stream = nullptr;
     bool scratch_busy = false;
     std::mutex mu;
-    std::string err;
     std::atomic<uint64_t> launches{0};
     size_t chunk = 1 << 16;          // gates per host-staged chunk
 };
 
 namespace {
 
-int fail(tfhe_b200_ctx* c, int code, const std::string& msg) {
-    if (c) c->err = msg; else g_create_error = msg;
+// The text of the last error is kept per calling thread (errno style): a failing call on one thread never
+// touches a string another thread may be reading through tfhe_b200_last_error.
+int fail(tfhe_b200_ctx*, int code, const std::string& msg) {
+    g_create_error = msg;
     return code;
 }
 
@@ -364,7 +365,10 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
     c->lowlat = env_int("TFHE_B200_LOWLAT", 1);
     c->ks_tile = env_int("TFHE_B200_KS_TILE", 1);
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) c->sm_count = prop.multiProcessorCount; }
-    c->chunk = (size_t)env_int("TFHE_B200_CHUNK", 1 << 16);
+    {   // gates per host-staged chunk: at least one wave of CTAs, never zero or negative
+        const long long v = env_int("TFHE_B200_CHUNK", 1 << 16);
+        c->chunk = (size_t)std::max<long long>(v, (long long)4 * c->sm_count);
+    }
     ctx = c;
     cudaError_t e = cudaEventCreateWithFlags(&c->scratch_ev, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
@@ -375,7 +379,7 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming);
     }
-    if (e != cudaSuccess) { delete c; return fail(nullptr, TFHE_B200_ECUDA, cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { tfhe_b200_destroy(c); return fail(nullptr, TFHE_B200_ECUDA, cudaGetErrorString(e)); }
     // twiddle table E[x] = exp(-i*pi*x/1024), computed in long double
     std::vector<double2> E(2048);
     for (int x = 0; x < 2048; x++) {
@@ -407,7 +411,7 @@ void tfhe_b200_destroy(tfhe_b200_ctx* c) {
     delete c;
 }
 
-const char* tfhe_b200_last_error(const tfhe_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+const char* tfhe_b200_last_error(const tfhe_b200_ctx*) { return g_create_error.c_str(); }
 uint64_t tfhe_b200_kernel_launches(const tfhe_b200_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 
 int tfhe_b200_synchronize(tfhe_b200_ctx* ctx) {
@@ -477,9 +481,10 @@ int tfhe_b200_load_ksk(tfhe_b200_ctx* ctx, const int32_t* ksk) {
 // ---- single-key, device buffers ---------------------------------------------------------------------
 int tfhe_b200_gate_batch_dev(tfhe_b200_ctx* ctx, int op, const int32_t* x, const int32_t* y, const int32_t* z,
                              int32_t* out, size_t count, void* stream) {
+    if (!ctx) return TFHE_B200_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
     int rc = check_single(ctx, true, true);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t wu = (size_t)ctx->P.N * ctx->P.k + 1;
     if ((rc = reserve(ctx, ctx->bu1, (op == TFHE_B200_MUX ? 2 : 1) * count * wu * 4))) return rc;
     ScratchGuard guard(ctx, (cudaStream_t)stream);
@@ -488,16 +493,18 @@ int tfhe_b200_gate_batch_dev(tfhe_b200_ctx* ctx, int op, const int32_t* x, const
 
 int tfhe_b200_bootstrap_wo_ks_batch_dev(tfhe_b200_ctx* ctx, int32_t mu, const int32_t* x, int32_t* out, size_t count,
                                         void* stream) {
+    if (!ctx) return TFHE_B200_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
     int rc = check_single(ctx, true, false);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(ctx->mu);
     return bootstrap_wo_ks_dev(ctx, x, nullptr, 1, 0, 0, mu, out, count, (cudaStream_t)stream);
 }
 
 int tfhe_b200_keyswitch_batch_dev(tfhe_b200_ctx* ctx, const int32_t* in, int32_t* out, size_t count, void* stream) {
+    if (!ctx) return TFHE_B200_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
     int rc = check_single(ctx, false, true);
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(ctx->mu);
     return launch_keyswitch(ctx, in, out, count, (cudaStream_t)stream);
 }
 
@@ -517,6 +524,17 @@ static int host_chunks(tfhe_b200_ctx* ctx, const int32_t* const hin[3], const si
     size_t chunk = ctx->chunk;
     if (count <= chunk && count >= 8 * wave) chunk = ((count + 3) / 4 + wave - 1) / wave * wave;
     bool used[2] = {false, false};
+    // The copy-out of chunk i is issued only after the kernels of chunk i+1 have been queued.  The caller's buffers
+    // may be PAGEABLE (a Julia Matrix{Int32}, a plain numpy array): cudaMemcpyAsync then blocks the host until the
+    // copy has been staged (H2D) or has finished (D2H).  Issued in this order, the host blocks while the device is
+    // busy with the next chunk, so the pipeline keeps its overlap with pageable memory too.
+    size_t prev_off = 0, prev_cnt = 0; int prev_slot = -1;
+    auto copy_out = [&](int slot, size_t off, size_t cnt) -> int {
+        CU(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[slot], 0));
+        CU(cudaMemcpyAsync(hout + off * wout, bo[slot]->p, cnt * wout * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
+        CU(cudaEventRecord(ctx->ev_out[slot], ctx->copy_out));
+        return 0;
+    };
     size_t idx = 0;
     for (size_t off = 0; off < count; off += chunk, idx++) {
         const int slot = (int)(idx & 1);
@@ -536,11 +554,11 @@ static int host_chunks(tfhe_b200_ctx* ctx, const int32_t* const hin[3], const si
         if (used[slot]) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[slot], 0));     // output of chunk idx-2 copied out
         if ((rc = body(din[0], din[1], din[2], (int32_t*)bo[slot]->p, cnt))) return rc;
         CU(cudaEventRecord(ctx->ev_done[slot], ctx->stream));
-        CU(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_done[slot], 0));
-        CU(cudaMemcpyAsync(hout + off * wout, bo[slot]->p, cnt * wout * 4, cudaMemcpyDeviceToHost, ctx->copy_out));
-        CU(cudaEventRecord(ctx->ev_out[slot], ctx->copy_out));
+        if (prev_slot >= 0 && (rc = copy_out(prev_slot, prev_off, prev_cnt))) return rc;
+        prev_slot = slot; prev_off = off; prev_cnt = cnt;
         used[slot] = true;
     }
+    if (prev_slot >= 0) { int rc = copy_out(prev_slot, prev_off, prev_cnt); if (rc) return rc; }
     CU(cudaStreamSynchronize(ctx->copy_out));
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -548,10 +566,11 @@ static int host_chunks(tfhe_b200_ctx* ctx, const int32_t* const hin[3], const si
 
 int tfhe_b200_gate_batch(tfhe_b200_ctx* ctx, int op, const int32_t* x, const int32_t* y, const int32_t* z,
                          int32_t* out, size_t count) {
+    if (!ctx) return TFHE_B200_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
     int rc = check_single(ctx, true, true);
     if (rc) return rc;
     if (!out) return fail(ctx, TFHE_B200_EINVAL, "null output");
-    std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t w = (size_t)ctx->P.n + 1, wu = (size_t)ctx->P.N * ctx->P.k + 1;
     const int32_t* hin[3] = {x, y, z};
     const size_t win[3] = {w, w, w};
@@ -563,10 +582,11 @@ int tfhe_b200_gate_batch(tfhe_b200_ctx* ctx, int op, const int32_t* x, const int
 }
 
 int tfhe_b200_bootstrap_wo_ks_batch(tfhe_b200_ctx* ctx, int32_t mu, const int32_t* x, int32_t* out, size_t count) {
+    if (!ctx) return TFHE_B200_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
     int rc = check_single(ctx, true, false);
     if (rc) return rc;
     if (!x || !out) return fail(ctx, TFHE_B200_EINVAL, "null argument");
-    std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t w = (size_t)ctx->P.n + 1, wu = (size_t)ctx->P.N * ctx->P.k + 1;
     const int32_t* hin[3] = {x, nullptr, nullptr};
     const size_t win[3] = {w, 0, 0};
@@ -576,10 +596,11 @@ int tfhe_b200_bootstrap_wo_ks_batch(tfhe_b200_ctx* ctx, int32_t mu, const int32_
 }
 
 int tfhe_b200_keyswitch_batch(tfhe_b200_ctx* ctx, const int32_t* in, int32_t* out, size_t count) {
+    if (!ctx) return TFHE_B200_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
     int rc = check_single(ctx, false, true);
     if (rc) return rc;
     if (!in || !out) return fail(ctx, TFHE_B200_EINVAL, "null argument");
-    std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t w = (size_t)ctx->P.n + 1, wu = (size_t)ctx->P.N * ctx->P.k + 1;
     const int32_t* hin[3] = {in, nullptr, nullptr};
     const size_t win[3] = {wu, 0, 0};
@@ -589,10 +610,11 @@ int tfhe_b200_keyswitch_batch(tfhe_b200_ctx* ctx, const int32_t* in, int32_t* ou
 }
 
 int tfhe_b200_bootstrap_batch(tfhe_b200_ctx* ctx, int32_t mu, const int32_t* x, int32_t* out, size_t count) {
+    if (!ctx) return TFHE_B200_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
     int rc = check_single(ctx, true, true);
     if (rc) return rc;
     if (!x || !out) return fail(ctx, TFHE_B200_EINVAL, "null argument");
-    std::lock_guard<std::mutex> lk(ctx->mu);
     const size_t w = (size_t)ctx->P.n + 1, wu = (size_t)ctx->P.N * ctx->P.k + 1;
     const int32_t* hin[3] = {x, nullptr, nullptr};
     const size_t win[3] = {w, 0, 0};
@@ -606,12 +628,13 @@ int tfhe_b200_bootstrap_batch(tfhe_b200_ctx* ctx, int32_t mu, const int32_t* x, 
 
 int tfhe_b200_extern_product_batch(tfhe_b200_ctx* ctx, const int32_t* acc, const int32_t* bk_index, int32_t* out,
                                    size_t count) {
+    if (!ctx) return TFHE_B200_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
     int rc = check_single(ctx, true, false);
     if (rc) return rc;
     if (!acc || !bk_index || !out) return fail(ctx, TFHE_B200_EINVAL, "null argument");
     for (size_t g = 0; g < count; g++)
         if (bk_index[g] < 0 || bk_index[g] >= ctx->P.n) return fail(ctx, TFHE_B200_EINVAL, "bk_index out of range");
-    std::lock_guard<std::mutex> lk(ctx->mu);
     const int32_t* hin[3] = {acc, bk_index, nullptr};
     const size_t win[3] = {2 * (size_t)kN, 1, 0};
     return host_chunks(ctx, hin, win, out, 2 * (size_t)kN, count, [&](int32_t* dacc, int32_t* didx, int32_t*, int32_t* dout, size_t cnt) {
@@ -621,11 +644,12 @@ int tfhe_b200_extern_product_batch(tfhe_b200_ctx* ctx, const int32_t* acc, const
 
 int tfhe_b200_blind_rotate_batch(tfhe_b200_ctx* ctx, const int32_t* acc_in, const int32_t* bara, int32_t n_iter,
                                  int32_t* acc_out, size_t count) {
+    if (!ctx) return TFHE_B200_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
     int rc = check_single(ctx, true, false);
     if (rc) return rc;
     if (!acc_in || !bara || !acc_out) return fail(ctx, TFHE_B200_EINVAL, "null argument");
     if (n_iter < 0 || n_iter > ctx->P.n) return fail(ctx, TFHE_B200_EINVAL, "n_iter out of range");
-    std::lock_guard<std::mutex> lk(ctx->mu);
     const int32_t* hin[3] = {acc_in, bara, nullptr};
     const size_t win[3] = {2 * (size_t)kN, (size_t)ctx->P.n, 0};
     return host_chunks(ctx, hin, win, acc_out, 2 * (size_t)kN, count, [&](int32_t* dacc, int32_t* dbara, int32_t*, int32_t* dout, size_t cnt) {
@@ -637,9 +661,9 @@ int tfhe_b200_blind_rotate_batch(tfhe_b200_ctx* ctx, const int32_t* acc_in, cons
 
 int tfhe_b200_polymul_batch(tfhe_b200_ctx* ctx, const int32_t* x, const int32_t* y, int32_t* out, size_t count) {
     if (!ctx) return TFHE_B200_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
     if (!x || !y || !out) return fail(ctx, TFHE_B200_EINVAL, "null argument");
     CU(cudaSetDevice(ctx->device));
-    std::lock_guard<std::mutex> lk(ctx->mu);
     const int32_t* hin[3] = {x, y, nullptr};
     const size_t win[3] = {(size_t)kN, (size_t)kN, 0};
     return host_chunks(ctx, hin, win, out, (size_t)kN, count, [&](int32_t* dx, int32_t* dy, int32_t*, int32_t* dout, size_t cnt) {
@@ -655,8 +679,8 @@ int tfhe_b200_polymul_batch(tfhe_b200_ctx* ctx, const int32_t* x, const int32_t*
 // ---- measurement helper -------------------------------------------------------------------------------
 int tfhe_b200_measure_fp64_tflops(tfhe_b200_ctx* ctx, double* out_tflops) {
     if (!ctx || !out_tflops) return TFHE_B200_EINVAL;
-    CU(cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, ctx->device));
     const int blocks = prop.multiProcessorCount * 4, threads = 512, iters = 8192;
