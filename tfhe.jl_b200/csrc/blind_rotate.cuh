@@ -48,6 +48,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     } while (!done);
 }
+// The same wait without the hardware suspend: mbarrier.try_wait parks the warp until the phase completes OR a
+// system-dependent time limit expires; a warp that starts waiting shortly before a bulk copy lands was measured to
+// lose several hundred cycles that way (clock64 probe).  test_wait only polls.
+__device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
 // global -> shared bulk copy (TMA, no tensor map needed for a contiguous 1-D block), completion on an mbarrier
 __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -64,41 +75,93 @@ constexpr int kChunkBytes = kChunkElems * 16;     // 16 KB
 // sub-partition and cap every thread at 168 registers (16K registers per sub-partition).
 // ORDER == 0: chunks are consumed in the order (c, r, half); ORDER == 1 (two-piece transforms, output-stationary
 // step): (c', c, r) — all digit polynomials against the two pieces of output component c' = 0, then c' = 1.
-template <int L, int NP, int STAGES, int ORDER = 0> struct BkFromRing {
+// LA = look-ahead in chunks (0: STAGES - 1, the deepest the ring allows; then the producer refills the stage released
+// one chunk ago and has to wait for the slowest group; with LA < STAGES - 1 the stage it refills was released
+// STAGES - 1 - LA chunks earlier).  POLL: consumers poll the full barrier instead of the suspending try_wait.
+// DIST: the refills are issued by the warps in turn (lane 0 of warp j % NW issues the j-th refill) instead of by
+// thread 0 alone, and every consumer tests the NEXT chunk's barrier one chunk early.  Measured with the clock64 probe
+// (DESIGN.md): an mbarrier test costs 100-150 cycles even when the phase is long complete; with one producer thread
+// that latency (twice per chunk: empty + full) plus the issue code made warp 0 the straggler of the CTA (8.2 k cycles
+// in the multiply-accumulate phase against 5.9 k for its sibling warp) and every other group waited for it.
+template <int L, int NP, int STAGES, int ORDER = 0, int PROBE = 0, int LA_ = 0, int POLL = 0, int DIST = 0> struct BkFromRing {
     static constexpr int kChunksPerIter = 2 * L * NP;
+    static constexpr int LA = LA_ ? LA_ : STAGES - 1;
+    static_assert(LA >= 1 && LA <= STAGES - 1, "look-ahead must leave one stage to the consumers");
     const double2* ring; uint64_t* full; uint64_t* empty;
     const double2* bk;        // start of the key, [n_iter][kChunksPerIter] chunks
     int total;                // chunks in the whole walk
     int k;                    // sequence number of the next chunk to consume
     int stage; uint32_t phase;
-    bool producer;
+    bool producer;            // DIST == 0: thread 0 of the CTA;  DIST == 1: lane 0 of every warp
+    long long w_full = 0, w_empty = 0, w_first = 0;   // PROBE: cycles spent waiting (all chunks / producer / first chunk of a pass)
+    // producer cursor: the next chunk to issue (sequence number, its stage, how often that stage has been used, its
+    // position (iteration, index in the iteration)) — advanced incrementally, no division in the loop.  With DIST every
+    // thread advances the cursor (the values are CTA-uniform) and `turn` names the warp whose lane 0 issues.
+    int iss = 0, iss_stage = 0, iss_round = 0, iss_i = 0, iss_q = 0;
+    int turn = 0, warp = 0, nwarps = 1;
+    uint32_t ready_next = 0;  // DIST: result of the early test of the next chunk's full barrier
 
-    // sequence number -> offset of the chunk in memory: consumption order is (c, r, half), storage (r, c, half)
-    __device__ __forceinline__ size_t chunk_offset(int seq) const {
-        int i = seq / kChunksPerIter, q = seq % kChunksPerIter;
+    // index in the iteration (consumption order) -> chunk inside the stored row: storage order is (r, c, half)
+    static __device__ __forceinline__ int stored_index(int q) {
         int h, cr;
         if (ORDER == 0) { h = q % NP; cr = q / NP; } else { h = q / (2 * L); cr = q % (2 * L); }
-        int r = cr % L, c = cr / L;
-        return ((size_t)i * kChunksPerIter + (size_t)((r * 2 + c) * NP + h)) * kChunkElems;
+        const int r = cr % L, c = cr / L;
+        return (r * 2 + c) * NP + h;
     }
-    __device__ __forceinline__ void issue(int seq) {
-        const int s = seq % STAGES;
-        mbar_arrive_expect_tx(full + s, kChunkBytes);
-        bulk_copy_g2s(const_cast<double2*>(ring) + (size_t)s * kChunkElems, bk + chunk_offset(seq), kChunkBytes, full + s);
+    __device__ __forceinline__ void issue_now() {
+        const size_t off = ((size_t)iss_i * kChunksPerIter + (size_t)stored_index(iss_q)) * kChunkElems;
+        mbar_arrive_expect_tx(full + iss_stage, kChunkBytes);
+        bulk_copy_g2s(const_cast<double2*>(ring) + (size_t)iss_stage * kChunkElems, bk + off, kChunkBytes, full + iss_stage);
+    }
+    __device__ __forceinline__ void advance() {
+        iss++;
+        if (++iss_stage == STAGES) { iss_stage = 0; iss_round++; }
+        if (++iss_q == kChunksPerIter) { iss_q = 0; iss_i++; }
+        if (DIST) { if (++turn == nwarps) turn = 0; }
     }
     __device__ __forceinline__ void prologue() {
-        if (producer)
-            for (int seq = 0; seq < STAGES - 1 && seq < total; seq++) issue(seq);
-    }
-    __device__ __forceinline__ const double2* acquire(int /*chunk: consumption order is fixed*/) {
-        if (producer) {
-            const int seq = k + STAGES - 1;
-            if (seq < total) {
-                if (k >= 1) mbar_wait(empty + (seq % STAGES), ((k - 1) / STAGES) & 1);
-                issue(seq);
-            }
+        while (iss < LA && iss < total) {
+            if (producer && (!DIST || turn == warp)) issue_now();
+            if (!DIST && !producer) break;   // only the producer thread keeps a cursor
+            advance();
         }
-        mbar_wait(full + stage, phase);
+    }
+    static __device__ __forceinline__ uint32_t test(uint64_t* bar, uint32_t parity) {
+        uint32_t done;
+        asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        return done;
+    }
+    __device__ __forceinline__ const double2* acquire(int first_of_pass /*consumption order is fixed*/) {
+        if (DIST) {
+            if (iss < total) {   // iss == k + LA: CTA-uniform
+                if (producer && turn == warp) {
+                    long long c0 = 0;
+                    if (PROBE) c0 = clock64();
+                    if (iss_round >= 1) mbar_wait(empty + iss_stage, (uint32_t)(iss_round - 1) & 1u);
+                    if (PROBE) w_empty += clock64() - c0;
+                    issue_now();
+                }
+                advance();
+            }
+        } else if (producer && iss < total) {
+            long long c0 = 0;
+            if (PROBE) c0 = clock64();
+            // the stage's previous occupant (chunk iss - STAGES) must have been released by every warp
+            if (iss_round >= 1) mbar_wait(empty + iss_stage, (uint32_t)(iss_round - 1) & 1u);
+            if (PROBE) w_empty += clock64() - c0;
+            issue_now();
+            advance();
+        }
+        long long c1 = 0;
+        if (PROBE) c1 = clock64();
+        if (DIST) {
+            if (!ready_next) mbar_wait_poll(full + stage, phase);
+            // test the following chunk now; the answer is back long before the next acquire needs it
+            const int ns = stage + 1 == STAGES ? 0 : stage + 1;
+            ready_next = test(full + ns, ns == 0 ? phase ^ 1u : phase);
+        } else if (POLL) mbar_wait_poll(full + stage, phase); else mbar_wait(full + stage, phase);
+        if (PROBE) { const long long d = clock64() - c1; w_full += d; if (first_of_pass) w_first += d; }
         return ring + (size_t)stage * kChunkElems;
     }
     __device__ __forceinline__ void release() {
@@ -252,12 +315,14 @@ __device__ __forceinline__ void tmem_ld_spectrum_finish(int (&r0)[16], int (&r1)
     }
 }
 
-template <int L, int BGBIT, int SYNC, class BK, class W>
+template <int L, int BGBIT, int SYNC, int PROBE, class BK, class W>
 __device__ __forceinline__ void extern_product_step_os(int32_t* acc, int abar, BK& bk, const W& w, double2* X1, double2* X2,
-                                                       uint32_t tm, int t, int bar_id) {
+                                                       uint32_t tm, int t, int bar_id, long long (&pr)[4]) {
     constexpr int Q = 2 * L;
     constexpr uint32_t offset = decomp_offset<L, BGBIT>();
     const int s = abar & 2047;
+    long long c0 = 0, c1 = 0;
+    if (PROBE) c0 = clock64();
     // ---- phase 1: the Q forward transforms ----
 #pragma unroll 1
     for (int c = 0; c < 2; c++) {
@@ -281,9 +346,11 @@ __device__ __forceinline__ void extern_product_step_os(int32_t* acc, int abar, B
         }
     }
     tmem_wait_st();   // this thread's F_q have landed; every acc read of the group precedes the last transform's barrier
+    if (PROBE) { c1 = clock64(); pr[0] += c1 - c0; }
     // ---- phase 2: one output component at a time ----
 #pragma unroll 1
     for (int c2 = 0; c2 < 2; c2++) {
+        if (PROBE) c0 = clock64();
         double2 lo[8], hi[8];
 #pragma unroll
         for (int e = 0; e < 8; e++) { lo[e] = make_double2(0.0, 0.0); hi[e] = make_double2(0.0, 0.0); }
@@ -294,13 +361,14 @@ __device__ __forceinline__ void extern_product_step_os(int32_t* acc, int abar, B
             double2 F[8];
             tmem_ld_spectrum_finish(r0, r1, F);
             if (q + 1 < Q) tmem_ld_spectrum_raw(tm + (uint32_t)((q + 1) * 32), r0, r1);   // in flight behind the MAC below
-            const double2* b = bk.acquire(0) + t;
+            const double2* b = bk.acquire(q == 0) + t;
 #pragma unroll
             for (int e = 0; e < 8; e++) cmac(lo[e], F[e], BK::load(b + e * 64));             // tgsw.jl:128
 #pragma unroll
             for (int e = 0; e < 8; e++) cmac(hi[e], F[e], BK::load(b + (8 + e) * 64));
             bk.release();
         }
+        if (PROBE) { c1 = clock64(); pr[1] += c1 - c0; }
         uint32_t rl[8], rh[8];
         fft512_inverse_t<SYNC>(lo, w, X1, X2, t, bar_id);
 #pragma unroll
@@ -313,8 +381,11 @@ __device__ __forceinline__ void extern_product_step_os(int32_t* acc, int abar, B
             p[j] = (int32_t)((uint32_t)p[j] + rl[m] + (round_to_u32_fast<true>(hi[m].x) << 16));                           // bootstrap.jl:22
             p[j + 512] = (int32_t)((uint32_t)p[j + 512] + rh[m] + (round_to_u32_fast<true>(-hi[m].y) << 16));
         }
+        if (PROBE) pr[2] += clock64() - c1;
     }
+    if (PROBE) c0 = clock64();
     group_sync(bar_id);   // the updated accumulator is visible to the whole group before the next rotation reads it
+    if (PROBE) pr[3] += clock64() - c0;
 }
 
 // ---- K4T: key switch of a TILE of 64 ciphertexts per CTA (keyswitch.jl:45-80) ---------------------------------
@@ -431,13 +502,18 @@ struct BlindRotateArgs {
     int32_t* out;            // MODE 0: [count][N+1] extracted LWE; MODE 1: [count][2][N]
     int n, n_iter, n_pad;
     unsigned long long count;
+    unsigned long long* probe;   // development: clock64 phase probe of the OPT bit-3 kernel variants (else null)
 };
 
 // per-group shared memory: X1 + X2 + acc (+ bara, n_pad words)
 __host__ __device__ constexpr int group_smem_bytes(int /*NP*/) { return (kSpectrum + kX2Elems) * 16 + 2 * kN * 4; }
-__host__ __device__ constexpr size_t br_smem_bytes(int NP, int G, int STAGES, int n_pad, int TM = 0) {
-    // TM == 3 (output-stationary step, SYNC == 1 transforms): a second X1 buffer per group
-    return (size_t)STAGES * kChunkBytes + 128 + (size_t)G * (group_smem_bytes(NP) + (TM == 3 ? kSpectrum * 16 : 0) + n_pad * 4);
+// TM == 3 (output-stationary step): two X1 buffers per group, used alternately (SYNC == 1 transforms); with OPT bit 1
+// (SYNC == 2 transforms) the second exchange happens in place and there is no X2 buffer
+__host__ __device__ constexpr size_t br_group_bytes(int NP, int TM, int OPT) {
+    return TM == 3 ? (size_t)2 * kSpectrum * 16 + ((OPT & 2) ? 0 : kX2Elems * 16) + 2 * kN * 4 : (size_t)group_smem_bytes(NP);
+}
+__host__ __device__ constexpr size_t br_smem_bytes(int NP, int G, int STAGES, int n_pad, int TM = 0, int OPT = 0) {
+    return (size_t)STAGES * kChunkBytes + 128 + (size_t)G * (br_group_bytes(NP, TM, OPT) + n_pad * 4);
 }
 
 // TMEM columns to allocate when the accumulators live in tensor memory: warps that share a lane quarter
@@ -449,8 +525,13 @@ __host__ __device__ constexpr int br_tmem_cols(int NP, int G, int L = 2, int TM 
     return c;
 }
 
-template <int L, int BGBIT, int NP, int G, int STAGES, int MODE, int TM = 0>
+// OPT (TM == 3 only): bit 0 = consumers poll the key ring (no suspending try_wait); bit 1 = in-place second exchange
+// (SYNC == 2 transforms, no X2 buffer: room for a deeper ring); bit 3 = clock64 phase probe (development; writes
+// A.probe); bit 2 = ring refills issued by the warps in turn + early barrier test; bits 4-6 = look-ahead of the
+// ring producer in chunks (0 = STAGES - 1)
+template <int L, int BGBIT, int NP, int G, int STAGES, int MODE, int TM = 0, int OPT = 0>
 __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs A) {
+    constexpr int PROBE = (OPT >> 3) & 1, POLL = OPT & 1, SYNCM = (OPT & 2) ? 2 : 1, LA = (OPT >> 4) & 7, DIST = (OPT >> 2) & 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t s_tmem_base;
     // TM: 0 = accumulators in registers, 1 = all in TMEM, 2 = component 1 in TMEM,
@@ -459,7 +540,7 @@ __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs
     static_assert(TM != 3 || NP == 2, "the output-stationary step is the two-piece path");
     constexpr int kTmemCols = br_tmem_cols(NP, G, L, TM);
     static_assert(kTmemCols <= 512, "tensor memory: too many gates per CTA");
-    constexpr size_t kGroupBytes = group_smem_bytes(NP) + (TM == 3 ? kSpectrum * 16 : 0);
+    constexpr size_t kGroupBytes = br_group_bytes(NP, TM, OPT);
     if (kUseTmem) {
         if ((threadIdx.x >> 5) == 0) tmem_alloc<kTmemCols>(&s_tmem_base);
         tmem_fence_before_sync();
@@ -480,7 +561,9 @@ __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs
         const int warp = threadIdx.x >> 5;
         tm = s_tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * br_tmem_cols_per_warp(NP, L, TM));
     }
-    BkFromRing<L, NP, STAGES, TM == 3 ? 1 : 0> bk{ring, full, empty, A.bk_fft, A.n_iter * 2 * L * NP, 0, 0, 0u, threadIdx.x == 0};
+    BkFromRing<L, NP, STAGES, TM == 3 ? 1 : 0, PROBE, LA, POLL, DIST> bk{ring, full, empty, A.bk_fft, A.n_iter * 2 * L * NP, 0, 0, 0u,
+                                                                            DIST ? (threadIdx.x & 31) == 0 : threadIdx.x == 0};
+    if (DIST) { bk.warp = threadIdx.x >> 5; bk.nwarps = 2 * G; }
     bk.prologue();   // the first STAGES-1 chunks are in flight while the gate prologue below runs
 
     // ---------------- consumers: one 64-thread group per gate ----------------
@@ -488,8 +571,8 @@ __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs
     const int bar_id = grp + 1;
     unsigned char* base = groups + (size_t)grp * (kGroupBytes + A.n_pad * 4);
     double2* X1 = reinterpret_cast<double2*>(base);                      // TM == 3: two buffers, used alternately
-    double2* X2 = X1 + (TM == 3 ? 2 : 1) * kSpectrum;
-    int32_t* acc = reinterpret_cast<int32_t*>(X2 + kX2Elems);
+    double2* X2 = X1 + (TM == 3 ? 2 : 1) * kSpectrum;                   // TM == 3 with OPT bit 1: unused (in-place exchange)
+    int32_t* acc = reinterpret_cast<int32_t*>(X2 + ((TM == 3 && (OPT & 2)) ? 0 : kX2Elems));
     int32_t* bara = acc + 2 * kN;
     const unsigned long long g = (unsigned long long)blockIdx.x * G + grp;
     const bool valid = g < A.count;   // a group without a gate still walks the ring (on zeros) to keep the lockstep
@@ -528,13 +611,23 @@ __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs
     }
     group_sync(bar_id);
 
+    long long pr[4] = {0, 0, 0, 0};
+    long long t_start = 0;
+    if (PROBE) t_start = clock64();
 #pragma unroll 1
     for (int i = 0; i < A.n_iter; i++) {   // bootstrap.jl:19-23
-        if constexpr (TM == 3) extern_product_step_os<L, BGBIT, 1>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id);
+        if constexpr (TM == 3) extern_product_step_os<L, BGBIT, SYNCM, PROBE>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id, pr);
         else if constexpr (TM != 0) extern_product_step_tmem<L, BGBIT, NP, (TM == 2 && NP == 2) ? 1 : 0>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id);
         else extern_product_step<L, BGBIT, NP, true, true>(acc, bara[i], bk, w, X1, X2, t, bar_id);
     }
 
+    if (PROBE && A.probe && blockIdx.x < 4 && (threadIdx.x & 31) == 0) {
+        // per warp: total, forward phase, MAC passes, inverse + update, end barrier, key waits (all / first of pass / producer)
+        unsigned long long* o = A.probe + ((size_t)blockIdx.x * 2 * G + (threadIdx.x >> 5)) * 8;
+        o[0] = (unsigned long long)(clock64() - t_start);
+        o[1] = pr[0]; o[2] = pr[1]; o[3] = pr[2]; o[4] = pr[3];
+        o[5] = bk.w_full; o[6] = bk.w_first; o[7] = bk.w_empty;
+    }
     if (!valid) {
     } else if (MODE == 0) {
         // tlwe_extract_sample (tlwe.jl:55-59): a = (p_0, -p_{N-1}, ..., -p_1), b = acc_b[0]

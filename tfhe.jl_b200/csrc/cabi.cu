@@ -111,10 +111,10 @@ int env_int(const char* name, int dflt) {
 }
 
 // ---- kernel dispatch ------------------------------------------------------------------------------
-template <int L, int BGBIT, int NP, int G, int STAGES, int MODE, int TM = 0>
+template <int L, int BGBIT, int NP, int G, int STAGES, int MODE, int TM = 0, int OPT = 0>
 int launch_br_g(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
-    auto kern = blind_rotate_kernel<L, BGBIT, NP, G, STAGES, MODE, TM>;
-    const size_t smem = br_smem_bytes(NP, G, STAGES, A.n_pad, TM);
+    auto kern = blind_rotate_kernel<L, BGBIT, NP, G, STAGES, MODE, TM, OPT>;
+    const size_t smem = br_smem_bytes(NP, G, STAGES, A.n_pad, TM, OPT);
     if (smem > 227 * 1024) return fail(ctx, TFHE_B200_EINVAL, "LWE dimension too large for the shared-memory layout");
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned grid = (unsigned)((A.count + G - 1) / G);
@@ -139,6 +139,31 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
             case 304:                                                                   // output-stationary step (two pieces only)
                 if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3>(ctx, A, s);
                 else return launch_br_g<L, BGBIT, NP, 4, 6, MODE>(ctx, A, s);
+            case 314: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 1>(ctx, A, s); else break;            // + polling
+            case 324: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 2>(ctx, A, s); else break;            // in-place exchange, 7 stages
+            case 334: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 3 | (4 << 4)>(ctx, A, s); else break; // + polling, look-ahead 4
+            case 344: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 2 | (4 << 4)>(ctx, A, s); else break; // look-ahead 4, try_wait
+            case 354: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 4>(ctx, A, s); else break;            // refills by the warps in turn + early test
+            case 364: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 6 | (5 << 4)>(ctx, A, s); else break; // + in-place exchange, 7 stages, look-ahead 5
+            case 1304:                                                                  // clock64 phase probe of 304 / 1334: of 354
+            case 1334:
+                if constexpr (NP == 2 && L == 2 && MODE == 0) {
+                    BlindRotateArgs B = A;
+                    CU(cudaMalloc(&B.probe, 4 * 8 * 8 * sizeof(unsigned long long)));
+                    int rc = ctx->G == 1304 ? launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 8>(ctx, B, s)
+                                            : launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 8 | 4>(ctx, B, s);
+                    std::vector<unsigned long long> h(4 * 8 * 8);
+                    CU(cudaStreamSynchronize(s));
+                    CU(cudaMemcpy(h.data(), B.probe, h.size() * 8, cudaMemcpyDeviceToHost));
+                    CU(cudaFree(B.probe));
+                    for (int b = 0; b < 2; b++)
+                        for (int w = 0; w < 8; w++) {
+                            const unsigned long long* o = &h[(b * 8 + w) * 8];
+                            fprintf(stderr, "probe cta %d warp %d: total %llu fwd %llu mac %llu inv %llu endbar %llu | key wait %llu first %llu producer %llu (cycles per iteration: %.0f)\n",
+                                    b, w, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], (double)o[0] / A.n_iter);
+                        }
+                    return rc;
+                } else return launch_br_g<L, BGBIT, NP, 4, 6, MODE>(ctx, A, s);
             default:
                 // measured (profiles/r1): with one 32-bit piece the 64 accumulator registers fit and registers win
                 // (148 k vs 135 k gates/s); with two pieces (128 registers) the fastest is component 0 in registers
@@ -166,6 +191,7 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
                     return launch_br_g<L, BGBIT, NP, 4, 6, MODE, TMv>(ctx, A, s);
                 }
         }
+        return launch_br_g<L, BGBIT, NP, 4, 6, MODE>(ctx, A, s);   // a two-piece-only variant was asked for with one piece
     }
 }
 template <int MODE>
