@@ -7,13 +7,17 @@
 
 A "step" is one pass of the hot path (gate prologue -> modswitch -> blind rotation -> extraction -> key
 switch) over one batch of NAND gates on synthetic 80-bit-parameter ciphertexts (BASELINE.json configs[1]:
-"batched NAND gate bootstrap sweep 1K-1M gates on 1 B200"; default 2^16 gates per GPU per step).
+"batched NAND gate bootstrap sweep 1K-1M gates on 1 B200"; default 2^17 gates per GPU per step, so that the
+8-GPU run holds 2^20 gates per step, inside configs[2]'s "1M-16M" range).
 
   value     gates/s with inputs already resident in HBM (tfhe_b200_gate_batch_dev), CUDA events on the
             launching stream, max over ranks.
   e2e       the same metric through the reference-facing host call tfhe_b200_gate_batch (what Julia's
             gate_nand.(…) binds to): pinned HOST buffers, host->device and device->host copies inside the
-            timed region.
+            timed region.  e2e_pageable: the same call on plain pageable numpy arrays (what a Julia Matrix{Int32} is).
+            e2e_single_process (N > 1): ONE process, tfhe_b200_multi_gate_batch over all N GPUs on the global batch.
+  value_unsplit  the device-resident value with the reference's own precision regime (one 32-bit piece, no proof).
+  mk_nand   MK-TFHE NAND gates/s for 2/4/8 parties on one GPU (BASELINE.json configs[4]).
   roofline  dominant kernel = blind_rotate_kernel: algorithmic FP64 flops (SURVEY.md §8d, 94.72 MFLOP per
             gate) / its CUDA-event duration, against the FP64 FMA peak measured live on this GPU.
   cpu_baseline  the oracle (a C restatement of TFHE.jl's algorithm, kind "port") on the host cores.
@@ -45,7 +49,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=1 << 16, help="gates per GPU per step")
+    ap.add_argument("--batch", type=int, default=1 << 17, help="gates per GPU per step")
+    ap.add_argument("--no-extras", action="store_true", help="skip value_unsplit, e2e_pageable, e2e_single_process and mk_nand")
     ap.add_argument("--unsplit", action="store_true", help="reference-precision FFT (one 32-bit piece) instead of the proven split")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -156,6 +161,33 @@ def run_reference(args, rank, world):
     }), file=OUT, flush=True)
 
 
+def mk_nand_rates(T, _cabi, torch, device):
+    """BASELINE.json configs[4]: MK-TFHE NAND gates/s for 2/4/8 parties on one GPU, device-resident operands, proven
+    (split) transform.  Throughput does not depend on the key VALUES, so key-shaped random material stands in for the
+    oracle's keygen (a minute for 8 parties); ciphertext parity of these kernels is tests/test_gpu_mk.py's job."""
+    from oracle import oracle as O
+    out = {}
+    for p, count in ((2, 2368), (4, 1184), (8, 592)):
+        P = O.MK_PARAMS[p]
+        rng = np.random.default_rng(p)
+        ctx = T.Context(n=P.n, l=P.l, bgbit=P.bgbit, t=P.t, basebit=P.basebit, parties=p, device=device)
+        ctx.load_bk(rng.integers(-2 ** 31, 2 ** 31, (p, P.n, P.l * (2 * p + 2), P.N), dtype=np.int32))
+        ctx.load_ksk(rng.integers(-2 ** 31, 2 ** 31, (p,) + P.ksk_shape, dtype=np.int32))
+        w = p * P.n + 1
+        dx = torch.from_numpy(rng.integers(-2 ** 31, 2 ** 31, (count, w), dtype=np.int32)).cuda()
+        dy = torch.from_numpy(rng.integers(-2 ** 31, 2 ** 31, (count, w), dtype=np.int32)).cuda()
+        do = torch.empty_like(dx)
+        s = torch.cuda.current_stream().cuda_stream
+        fn = lambda: ctx.mk_nand_dev(dx.data_ptr(), dy.data_ptr(), do.data_ptr(), count, stream=s)
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        out[str(p)] = {"gates_per_s": count / (e0.elapsed_time(e1) * 1e-3), "gates": count, "unit": "gates/s"}
+        ctx.close()
+        del dx, dy, do
+    return out
+
+
 def main():
     # stdout carries exactly ONE JSON line: keep a private handle on the real stdout and point fd 1 at stderr, so
     # that anything a library writes to stdout (NCCL prints its version banner there) cannot pollute it
@@ -259,6 +291,60 @@ def main():
     e2e_value = B * world * args.steps / float(e2e_s.item())
     assert np.array_equal(hout.numpy(), got), "host-buffer path and device-buffer path disagree"
 
+    # ---- extras measured on every rank (max over ranks): pageable host buffers, the unproven one-piece transform
+    extras = {}
+    if not args.no_extras:
+        px, py = np.array(x), np.array(y)                      # plain pageable arrays: what a Julia Matrix{Int32} is
+        pout = np.empty((B, W), dtype=np.int32)
+
+        def step_pageable():
+            rc = T.lib().tfhe_b200_gate_batch(ctx._h, O.NAND, px.ctypes.data, py.ctypes.data, None, pout.ctypes.data, B)
+            if rc:
+                raise RuntimeError(T.lib().tfhe_b200_last_error(ctx._h))
+
+        step_pageable()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(1, min(args.steps, 3))):
+            step_pageable()
+        barrier()
+        pg_s = torch.tensor([time.perf_counter() - t0], device="cuda")
+        if world > 1:
+            dist.all_reduce(pg_s, op=dist.ReduceOp.MAX)
+        assert np.array_equal(pout, got), "pageable host path and device path disagree"
+        extras["e2e_pageable"] = {"value": B * world * max(1, min(args.steps, 3)) / float(pg_s.item()), "unit": "gates/s",
+                                  "note": "tfhe_b200_gate_batch on plain pageable numpy arrays (no pinning by the caller)"}
+        if not args.unsplit:
+            uctx = T.Context(n=P.n, l=P.l, bgbit=P.bgbit, t=P.t, basebit=P.basebit, device=local_rank, flags=_cabi.FLAG_UNSPLIT_FFT)
+            uctx.load_bk(keys.bk); uctx.load_ksk(keys.ksk)
+            ustep = lambda: uctx.gate_dev(O.NAND, dx.data_ptr(), dy.data_ptr(), 0, dout.data_ptr(), B, stream=stream)
+            ustep()
+            ums = timed(ustep, max(1, min(args.steps, 3)))
+            assert np.array_equal(dout.cpu().numpy(), got), "one-piece transform and proven transform disagree"
+            extras["value_unsplit"] = {"value": B * world * max(1, min(args.steps, 3)) / (ums * 1e-3), "unit": "gates/s",
+                                       "note": "reference precision regime (polynomials.jl:138-140): one 32-bit piece, exact in every test, no proof"}
+            uctx.close()
+        if world > 1:
+            # ONE process driving all GPUs through the product's multi-device context; the other ranks stay idle
+            dist.barrier()
+            if rank == 0:
+                m = _cabi.MultiContext(n=P.n, l=P.l, bgbit=P.bgbit, t=P.t, basebit=P.basebit, devices=list(range(world)), flags=flags)
+                m.load_bk(keys.bk); m.load_ksk(keys.ksk)
+                gx = torch.from_numpy(np.tile(x, (world, 1))).pin_memory(); gy = torch.from_numpy(np.tile(y, (world, 1))).pin_memory()
+                gout = torch.empty((B * world, W), dtype=torch.int32).pin_memory()
+                run = lambda: m._ck(T.lib().tfhe_b200_multi_gate_batch(m._h, O.NAND, gx.data_ptr(), gy.data_ptr(), None, gout.data_ptr(), B * world))
+                run()
+                reps = max(1, min(args.steps, 3))
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    run()
+                sp = time.perf_counter() - t0
+                assert np.array_equal(gout.numpy()[:B], got) and np.array_equal(gout.numpy()[-B:], got), "multi-device context disagrees"
+                extras["e2e_single_process"] = {"value": B * world * reps / sp, "unit": "gates/s", "devices": m.devices,
+                                                "note": "one process, tfhe_b200_multi_gate_batch: host buffers in, host buffer out, batch sharded over all GPUs"}
+                m.close()
+            dist.barrier()
+
     if rank == 0:
         # ---- dominant kernel alone, CUDA events on its launching stream
         def br_only():
@@ -285,12 +371,8 @@ def main():
 
         lat = sorted(kernel_ms(one_gate, 1) for _ in range(9))[4]
         fp64_peak = ctx.measure_fp64_tflops()
+        lds_peak = ctx.measure_lds_gbps()
         achieved = W_FFT_FLOP_PER_GATE * B / (br_ms * 1e-3) / 1e12
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
         traffic, traffic_src = None, "no ncu capture committed for this launch size (profiles/traffic.json)"
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -299,8 +381,10 @@ def main():
                 traffic, traffic_src = ent["dram_bytes"], ent["source"]
         except (OSError, KeyError, ValueError):
             pass
-        hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
-        ks_gbs = Q_KSK_BYTES_PER_GATE * B / (ks_ms * 1e-3) / 1e9
+        # K4 (tiled): every ciphertext reads N*t table rows of `stride` words from shared memory
+        ks_tiled = B >= 4096
+        ks_smem_bytes = P.N * P.k * P.t * (((P.n + 1 + 31) & ~31) * 4)
+        ks_gbs = (ks_smem_bytes if ks_tiled else Q_KSK_BYTES_PER_GATE) * B / (ks_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "gates/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -318,10 +402,15 @@ def main():
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one blind_rotate_kernel launch of this size (bytes); " + traffic_src + "; keys are L2-resident, the kernel is not DRAM-bound",
                          "peak_source": "FP64 FMA rate measured live on this GPU (MEASURED_PEAKS.json has no FP64 entry); not tensor- or HBM-bound: keys are L2-resident",
                          "kernel_ms": br_ms, "algorithmic_flop_per_gate": W_FFT_FLOP_PER_GATE, "share_of_step": br_ms / (ms_total / args.steps)},
-            "roofline_keyswitch": {"bound": "hbm", "kernel": "keyswitch_tile_kernel" if B >= 4096 else "keyswitch_kernel", "achieved": ks_gbs, "peak": hbm_peak, "unit": "GB/s",
-                                   "frac": ks_gbs / hbm_peak, "peak_source": hbm_src + "; algorithmic bytes = table rows gathered per gate; the tile kernel streams the 50 MB table once per 64 ciphertexts through shared memory, so frac > 1 is expected (bound: shared-memory pipe)",
-                                   "kernel_ms": ks_ms, "algorithmic_bytes_per_gate": Q_KSK_BYTES_PER_GATE},
+            "roofline_keyswitch": {"bound": "smem" if ks_tiled else "l2", "kernel": "keyswitch_tile_kernel" if ks_tiled else "keyswitch_kernel",
+                                   "achieved": ks_gbs, "peak": lds_peak, "unit": "GB/s", "frac": ks_gbs / lds_peak,
+                                   "peak_source": "conflict-free LDS.128 read rate measured live on this GPU; the tile kernel streams the 50 MB table once per 64 ciphertexts "
+                                                  "through shared memory and every ciphertext reads N*t rows of it with LDS.128, so shared memory is the pipe that bounds it (not HBM)",
+                                   "kernel_ms": ks_ms, "algorithmic_bytes_per_gate": ks_smem_bytes if ks_tiled else Q_KSK_BYTES_PER_GATE},
         }
+        line.update(extras)
+        if world == 1 and not args.no_extras:
+            line["mk_nand"] = mk_nand_rates(T, _cabi, torch, local_rank)
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             octx = O.Context(keys)

@@ -106,6 +106,8 @@ uint64_t tfhe_b200_kernel_launches(const tfhe_b200_ctx* ctx);
 int tfhe_b200_synchronize(tfhe_b200_ctx* ctx);
 /* measured FP64 FMA throughput of the context's device (roofline denominator of the transform kernels) */
 int tfhe_b200_measure_fp64_tflops(tfhe_b200_ctx* ctx, double* out_tflops);
+/* measured conflict-free LDS.128 read rate of the context's device (roofline denominator of the tiled key switch) */
+int tfhe_b200_measure_lds_gbps(tfhe_b200_ctx* ctx, double* out_gbps);
 
 /* ---- key loading (K6) -------------------------------------------------------------------- */
 /* BootstrapKey (bootstrap.jl:1-16): takes the int32 coefficient form and performs

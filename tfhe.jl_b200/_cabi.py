@@ -61,6 +61,7 @@ def lib():
             "tfhe_b200_kernel_launches": (C.c_uint64, [vp]),
             "tfhe_b200_synchronize": (C.c_int, [vp]),
             "tfhe_b200_measure_fp64_tflops": (C.c_int, [vp, C.POINTER(C.c_double)]),
+            "tfhe_b200_measure_lds_gbps": (C.c_int, [vp, C.POINTER(C.c_double)]),
             "tfhe_b200_load_bk": (C.c_int, [vp, i32p]),
             "tfhe_b200_load_ksk": (C.c_int, [vp, i32p]),
             "tfhe_b200_gate_batch": (C.c_int, [vp, C.c_int, i32p, i32p, i32p, i32p, sz]),
@@ -163,6 +164,11 @@ class Context:
     def measure_fp64_tflops(self) -> float:
         v = C.c_double()
         self._ck(lib().tfhe_b200_measure_fp64_tflops(self._h, C.byref(v)))
+        return v.value
+
+    def measure_lds_gbps(self) -> float:
+        v = C.c_double()
+        self._ck(lib().tfhe_b200_measure_lds_gbps(self._h, C.byref(v)))
         return v.value
 
     # widths

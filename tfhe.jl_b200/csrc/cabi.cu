@@ -729,3 +729,30 @@ int tfhe_b200_measure_fp64_tflops(tfhe_b200_ctx* ctx, double* out_tflops) {
     *out_tflops = best;
     return 0;
 }
+
+int tfhe_b200_measure_lds_gbps(tfhe_b200_ctx* ctx, double* out_gbps) {
+    if (!ctx || !out_gbps) return TFHE_B200_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, ctx->device));
+    const int blocks = prop.multiProcessorCount * 4, threads = 512, iters = 4096;
+    int rc;
+    if ((rc = reserve(ctx, ctx->bout, (size_t)blocks * threads * sizeof(double)))) return rc;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        CU(cudaEventRecord(e0, ctx->stream));
+        lds_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((double*)ctx->bout.p, iters);
+        CU(cudaEventRecord(e1, ctx->stream));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        double gbps = (double)blocks * threads * iters * 8 * 16 / (ms * 1e-3) / 1e9;
+        if (rep > 0 && gbps > best) best = gbps;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *out_gbps = best;
+    return 0;
+}

@@ -387,6 +387,21 @@ __global__ void lincomb_kernel(const int32_t* __restrict__ x, const int32_t* __r
 }  // namespace tfhe_b200
 
 namespace tfhe_b200 {
+// Measures the shared-memory read rate with conflict-free LDS.128 (the roofline denominator of the tiled key switch,
+// which is bound by the shared-memory pipe, not by HBM).
+__global__ void lds_peak_kernel(double* out, int iters) {
+    __shared__ double2 buf[1024];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) buf[i] = make_double2(i, -i);
+    __syncthreads();
+    double2 acc = make_double2(0, 0);
+    int idx = threadIdx.x;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) { double2 v = buf[(idx + u * 64) & 1023]; acc.x += v.x; acc.y += v.y; }
+        idx = (idx + 1) & 1023;
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc.x + acc.y;
+}
 // Measures the FP64 FMA issue rate of the device (the roofline denominator of the transform kernels:
 // MEASURED_PEAKS.json only records HBM and bf16 peaks).  8 independent FMA chains per thread.
 __global__ void fp64_peak_kernel(double* out, double a, double b, int iters) {

@@ -1,25 +1,31 @@
 # TFHEB200.jl — Julia host layer over libtfhe_b200.so (the C ABI of include/tfhe_b200.h).
 #
-# Keeps the API surface of nucypher/TFHE.jl (src/TFHE.jl:24-61): make_key_pair, encrypt, decrypt, the
-# thirteen gate_* functions and the MK entry points, and adds batched array variants: an `LweSample` may
-# hold a Matrix{Int32}(n+1, count) (one ciphertext per column — exactly the [count][n+1] layout of the C
-# ABI), so `gate_nand(ck, x, y)` on batches is ONE `ccall` and one set of kernel launches.
+# Drop-in for the API surface of nucypher/TFHE.jl (src/TFHE.jl:24-61): the same exported names, the same
+# `LweSample` fields (`params`, `a`, `b`, `current_variance`, lwe.jl:21-29), the same broadcasting behaviour of keys
+# and samples (lwe.jl:32, api.jl:103,130), so the documented idiom
 #
-# This file is a 1:1 thin mirror of tfhe.jl_b200/api.py + _cabi.py (which the test-suite exercises through
-# ctypes).  Julia is not installed in the build image, so this wrapper is shipped untested; every call it
-# makes is a symbol the tests bind.  There is no CPU fallback: without the library / a GPU, calls throw.
+#     ciphertext1 = encrypt.(Ref(rng), secret_key, bits1)          # docs/src/manual.md:28-35
+#     cresult     = gate_xor.(cloud_key, ciphertext1, ciphertext2)
+#     result      = decrypt.(secret_key, cresult)
+#
+# and the `Array{LweSample,1}` signatures of examples/tutorial.jl:42-62 work unchanged — with one difference under the
+# hood: a broadcast over vectors of samples is intercepted (`Base.Broadcast.broadcasted`, below), packed into ONE
+# Matrix{Int32}(n+1, count) — byte for byte the [count][n+1] batch layout of the C ABI — and evaluated by ONE `ccall`
+# (one set of kernel launches for the whole vector, sharded over every GPU of a `CloudKey(...; devices = ...)`),
+# instead of one 1.7 ms bootstrap per element.  `LweBatch` exposes that matrix form directly for bulk work.
+#
+# Julia is not installed in the build image, so this file cannot be executed there; what CAN be checked without Julia is
+# checked by tests/test_julia_binding.py: every `ccall` below names a symbol declared in include/tfhe_b200.h with the
+# same arity and the same integer widths.  crosscheck.jl compares against genuine TFHE.jl when both are installed.
+# There is no CPU fallback: without the library or a GPU every call throws.
 #
 #     ENV["TFHE_B200_LIB"] = "/path/to/libtfhe_b200.so"   # default: ../libtfhe_b200.so next to this file
-#     using .TFHEB200, Random
-#     sk, ck = make_key_pair(MersenneTwister(123))
-#     x = encrypt(rng, sk, rand(Bool, 65536)); y = encrypt(rng, sk, rand(Bool, 65536))
-#     z = gate_nand(ck, x, y)            # 65 536 bootstrapped NANDs on the B200
-#     decrypt(sk, z)
 module TFHEB200
 
 using Random: AbstractRNG
 
-export make_key_pair, LweSample, SecretKey, CloudKey, encrypt, decrypt, tfhe_parameters_80, tfhe_parameters_128
+export make_key_pair, LweSample, LweBatch, SecretKey, CloudKey, SchemeParameters, encrypt, decrypt
+export tfhe_parameters_80, tfhe_parameters_128
 export gate_nand, gate_or, gate_and, gate_xor, gate_xnor, gate_not, gate_constant, gate_nor
 export gate_andny, gate_andyn, gate_orny, gate_oryn, gate_mux
 export SharedKey, CloudKeyPart, MKCloudKey, MKLweSample, mk_encrypt, mk_decrypt, mk_gate_nand
@@ -37,22 +43,37 @@ const FLAG_SPLIT_FFT = UInt32(0)
 const FLAG_UNSPLIT_FFT = UInt32(1)
 @enum GateOp NAND = 0 OR = 1 AND = 2 XOR = 3 XNOR = 4 NOT = 5 CONSTANT = 6 NOR = 7 ANDNY = 8 ANDYN = 9 ORNY = 10 ORYN = 11 MUX = 12
 
+last_error() = unsafe_string(ccall((:tfhe_b200_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL))
+multi_last_error() = unsafe_string(ccall((:tfhe_b200_multi_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL))
+
+"One parameter set + one evaluation-key set on one GPU (`multi == false`) or replicated over several (`multi == true`)."
 mutable struct Context
     handle::Ptr{Cvoid}
     params::CParams
-    function Context(p::CParams; device::Integer = 0, flags::UInt32 = FLAG_SPLIT_FFT)
+    multi::Bool
+    function Context(p::CParams; device::Integer = 0, devices::Union{Nothing, Vector{<:Integer}, Symbol} = nothing,
+                     flags::UInt32 = FLAG_SPLIT_FFT)
         h = Ref{Ptr{Cvoid}}(C_NULL)
-        rc = ccall((:tfhe_b200_create, LIB), Cint, (Ref{CParams}, Cint, UInt32, Ref{Ptr{Cvoid}}), p, device, flags, h)
-        rc == 0 || error("tfhe_b200_create: " * unsafe_string(ccall((:tfhe_b200_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
-        ctx = new(h[], p)
-        finalizer(c -> ccall((:tfhe_b200_destroy, LIB), Cvoid, (Ptr{Cvoid},), c.handle), ctx)
+        if devices === nothing
+            rc = ccall((:tfhe_b200_create, LIB), Cint, (Ref{CParams}, Cint, UInt32, Ref{Ptr{Cvoid}}), p, device, flags, h)
+            rc == 0 || error("tfhe_b200_create: " * last_error())
+            ctx = new(h[], p, false)
+            finalizer(c -> ccall((:tfhe_b200_destroy, LIB), Cvoid, (Ptr{Cvoid},), c.handle), ctx)
+            return ctx
+        end
+        ids = devices === :all ? Cint[] : Cint.(devices)        # empty list = every visible device
+        rc = GC.@preserve ids ccall((:tfhe_b200_multi_create, LIB), Cint, (Ref{CParams}, Ptr{Cint}, Cint, UInt32, Ref{Ptr{Cvoid}}),
+                                    p, isempty(ids) ? Ptr{Cint}(C_NULL) : pointer(ids), length(ids), flags, h)
+        rc == 0 || error("tfhe_b200_multi_create: " * multi_last_error())
+        ctx = new(h[], p, true)
+        finalizer(c -> ccall((:tfhe_b200_multi_destroy, LIB), Cvoid, (Ptr{Cvoid},), c.handle), ctx)
         ctx
     end
 end
 
 function check(ctx::Context, rc::Cint)                          # error codes -> Julia exceptions (SURVEY §5)
-    rc == 0 && return
-    error("tfhe_b200 error $rc: " * unsafe_string(ccall((:tfhe_b200_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx.handle)))
+    rc == 0 && return nothing
+    error("tfhe_b200 error $rc: " * (ctx.multi ? multi_last_error() : last_error()))
 end
 
 cptr(a::Array{Int32}) = pointer(a)
@@ -60,29 +81,83 @@ cptr(::Nothing) = Ptr{Int32}(C_NULL)
 
 # Julia arrays are column-major: Matrix{Int32}(n+1, count) IS the C layout [count][n+1].
 function c_gate(ctx::Context, op::GateOp, x, y, z, count::Integer)
-    out = Matrix{Int32}(undef, ctx.params.n * ctx.params.parties + 1, count)
-    GC.@preserve x y z out check(ctx, ccall((:tfhe_b200_gate_batch, LIB), Cint,
-        (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Csize_t),
-        ctx.handle, Int(op), cptr(x), cptr(y), cptr(z), out, count))
+    out = Matrix{Int32}(undef, Int(ctx.params.n) * Int(ctx.params.parties) + 1, count)
+    GC.@preserve x y z out begin
+        rc = if ctx.multi
+            ccall((:tfhe_b200_multi_gate_batch, LIB), Cint,
+                  (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Csize_t),
+                  ctx.handle, Int(op), cptr(x), cptr(y), cptr(z), pointer(out), count)
+        else
+            ccall((:tfhe_b200_gate_batch, LIB), Cint,
+                  (Ptr{Cvoid}, Cint, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Csize_t),
+                  ctx.handle, Int(op), cptr(x), cptr(y), cptr(z), pointer(out), count)
+        end
+        check(ctx, rc)
+    end
+    out
+end
+
+"bootstrap (bootstrap.jl:92-95) / mk_bootstrap (mk_internals.jl:512-515) of a batch with an arbitrary test-vector value"
+function c_bootstrap(ctx::Context, mu::Torus32, x::Matrix{Int32})
+    out = similar(x)
+    GC.@preserve x out begin
+        rc = if ctx.multi
+            ccall((:tfhe_b200_multi_bootstrap_batch, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int32}, Csize_t),
+                  ctx.handle, mu, pointer(x), pointer(out), size(x, 2))
+        elseif ctx.params.parties == 1
+            ccall((:tfhe_b200_bootstrap_batch, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int32}, Csize_t),
+                  ctx.handle, mu, pointer(x), pointer(out), size(x, 2))
+        else
+            ccall((:tfhe_b200_mk_bootstrap_batch, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int32}, Csize_t),
+                  ctx.handle, mu, pointer(x), pointer(out), size(x, 2))
+        end
+        check(ctx, rc)
+    end
     out
 end
 
 function c_polymul(ctx::Context, x::Matrix{Int32}, y::Matrix{Int32})     # transformed_mul, polynomials.jl:142-144
+    @assert !ctx.multi
     out = similar(x)
     GC.@preserve x y out check(ctx, ccall((:tfhe_b200_polymul_batch, LIB), Cint,
-        (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Csize_t), ctx.handle, x, y, out, size(x, 2)))
+        (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Csize_t), ctx.handle, pointer(x), pointer(y), pointer(out), size(x, 2)))
     out
 end
 
-load_bk!(ctx::Context, bk::Array{Int32}) = GC.@preserve bk check(ctx, ccall(
-    (ctx.params.parties == 1 ? :tfhe_b200_load_bk : :tfhe_b200_mk_load_bk, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}), ctx.handle, bk))
-load_ksk!(ctx::Context, ksk::Array{Int32}) = GC.@preserve ksk check(ctx, ccall(
-    (ctx.params.parties == 1 ? :tfhe_b200_load_ksk : :tfhe_b200_mk_load_ksk, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}), ctx.handle, ksk))
+function load_bk!(ctx::Context, bk::Array{Int32})
+    GC.@preserve bk begin
+        rc = if ctx.multi && ctx.params.parties == 1
+            ccall((:tfhe_b200_multi_load_bk, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}), ctx.handle, pointer(bk))
+        elseif ctx.multi
+            ccall((:tfhe_b200_multi_mk_load_bk, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}), ctx.handle, pointer(bk))
+        elseif ctx.params.parties == 1
+            ccall((:tfhe_b200_load_bk, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}), ctx.handle, pointer(bk))
+        else
+            ccall((:tfhe_b200_mk_load_bk, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}), ctx.handle, pointer(bk))
+        end
+        check(ctx, rc)
+    end
+end
+
+function load_ksk!(ctx::Context, ksk::Array{Int32})
+    GC.@preserve ksk begin
+        rc = if ctx.multi && ctx.params.parties == 1
+            ccall((:tfhe_b200_multi_load_ksk, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}), ctx.handle, pointer(ksk))
+        elseif ctx.multi
+            ccall((:tfhe_b200_multi_mk_load_ksk, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}), ctx.handle, pointer(ksk))
+        elseif ctx.params.parties == 1
+            ccall((:tfhe_b200_load_ksk, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}), ctx.handle, pointer(ksk))
+        else
+            ccall((:tfhe_b200_mk_load_ksk, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}), ctx.handle, pointer(ksk))
+        end
+        check(ctx, rc)
+    end
+end
 
 # ---------------------------------------------------------------------------------------------- numeric-functions.jl
 rand_uniform_bool(rng::AbstractRNG, dims...) = rand(rng, Int32(0):Int32(1), dims...)
 rand_uniform_torus32(rng::AbstractRNG, dims...) = rand(rng, Torus32, dims...)
-dtot32(d::Float64) = trunc(Int32, d * 2^32)
+dtot32(d::Float64) = trunc(Int32, d * 2^32)                    # numeric-functions.jl:51-53 (InexactError outside [-0.5, 0.5))
 rand_gaussian_torus32(rng::AbstractRNG, sigma::Float64, dims...) = dtot32.(randn(rng, dims...) .* sigma)
 encode_message(mu::Int, message_space::Int) = Torus32(mu) << (32 - trailing_zeros(message_space))
 
@@ -106,31 +181,57 @@ const mktfhe_parameters_8party = SchemeParameters(500, 0.012467, 1024, 1, 8, 4, 
 cparams(p::SchemeParameters, parties::Int) = CParams(p.lwe_size, p.tlwe_polynomial_degree, p.tlwe_mask_size,
     p.bs_decomp_length, p.bs_log2_base, p.ks_decomp_length, p.ks_log2_base, parties)
 
-"An encrypted bit (lwe.jl:21-29) or a batch of them: `data` is (n+1) or (n+1, count); rows 1:n = a, row n+1 = b."
-struct LweSample
-    data::Array{Int32}
+struct LweParams                                                # lwe.jl:1-8
+    size::Int
+end
+
+"An encrypted bit: the reference's structure, field for field (lwe.jl:21-29)."
+mutable struct LweSample
+    params::LweParams
+    a::Array{Torus32, 1}
+    b::Torus32
     current_variance::Float64
 end
-Base.length(x::LweSample) = size(x.data, 2)
-Base.getindex(x::LweSample, i) = LweSample(x.data[:, i], x.current_variance)
-Base.:+(x::LweSample, y::LweSample) = LweSample(x.data .+ y.data, x.current_variance + y.current_variance)   # lwe.jl:67-68
-Base.:-(x::LweSample, y::LweSample) = LweSample(x.data .- y.data, x.current_variance + y.current_variance)   # lwe.jl:71-72
-Base.:-(x::LweSample) = LweSample(.-x.data, x.current_variance)                                              # lwe.jl:74
+Base.Broadcast.broadcastable(lwe::LweSample) = (lwe,)           # lwe.jl:32
+Base.:+(x::LweSample, y::LweSample) = LweSample(x.params, x.a .+ y.a, x.b + y.b, x.current_variance + y.current_variance)   # lwe.jl:67-68
+Base.:-(x::LweSample, y::LweSample) = LweSample(x.params, x.a .- y.a, x.b - y.b, x.current_variance + y.current_variance)   # lwe.jl:71-72
+Base.:-(x::LweSample) = LweSample(x.params, .-x.a, -x.b, x.current_variance)                                                # lwe.jl:74
+Base.:*(x::LweSample, y::Integer) = LweSample(x.params, x.a .* Int32(y), x.b * Int32(y), x.current_variance * y^2)           # lwe.jl:77-82
+Base.:*(y::Integer, x::LweSample) = x * y
+
+"""
+A batch of encrypted bits in the C ABI's layout: `data` is (n+1, count), one ciphertext per column (rows 1:n = a,
+row n+1 = b).  `LweBatch(v)` packs a vector of samples, `collect(batch)` / `batch[i]` unpack.  All `gate_*` functions
+accept batches and evaluate them with one call into the library.
+"""
+struct LweBatch
+    data::Matrix{Int32}
+    current_variance::Float64
+end
+LweBatch(v::AbstractVector{LweSample}) =
+    LweBatch(isempty(v) ? Matrix{Int32}(undef, 1, 0) : hcat((vcat(s.a, s.b) for s in v)...), isempty(v) ? 0.0 : maximum(s.current_variance for s in v))
+Base.length(x::LweBatch) = size(x.data, 2)
+Base.getindex(x::LweBatch, i::Integer) = LweSample(LweParams(size(x.data, 1) - 1), x.data[1:end-1, i], x.data[end, i], x.current_variance)
+Base.collect(x::LweBatch) = [x[i] for i in 1:length(x)]
 
 struct SecretKey                                                # api.jl:92-100
     params::SchemeParameters
     key::Vector{Int32}
     SecretKey(rng::AbstractRNG, params::SchemeParameters) = new(params, rand_uniform_bool(rng, params.lwe_size))
 end
+Base.Broadcast.broadcastable(sk::SecretKey) = (sk,)             # api.jl:103
 
-# tlwe.jl:63-73 for `count` samples at once; the products S (*) a run on the GPU (kernel K1)
+# tlwe.jl:63-73 for `count` samples at once; the products S (*) a run on the GPU (kernel K1).
+# All sums stay in Int32 (wrap-around mod 2^32, as in the reference): `sum` over Int32 would widen to Int64.
 function tlwe_encrypt_zero(rng, ctx::Context, alpha::Float64, tlwe_key::Matrix{Int32}, count::Int)
     N, k = size(tlwe_key)
     a = rand_uniform_torus32(rng, N, k, count)
     b = rand_gaussian_torus32(rng, alpha, N, count)
     keys = repeat(reshape(tlwe_key, N, k, 1), 1, 1, count)
     prod = reshape(c_polymul(ctx, reshape(keys, N, k * count), reshape(a, N, k * count)), N, k, count)
-    b .+= dropdims(sum(prod, dims = 2), dims = 2)
+    for c in 1:k
+        b .+= view(prod, :, c, :)
+    end
     cat(a, reshape(b, N, 1, count), dims = 2)                   # (N, k+1, count)
 end
 
@@ -144,6 +245,8 @@ function bootstrap_key(rng, ctx, alpha, lwe_key::Vector{Int32}, tlwe_key::Matrix
     bk
 end
 
+wrapdot(a::AbstractVector{Int32}, key::AbstractVector{Int32}) = reduce(+, a .* key; init = Int32(0))      # Int32 wrap-around
+
 # keyswitch.jl:14-41; memory order [N*k][t][base-1][n+1]
 function keyswitch_key(rng, alpha, t::Int, basebit::Int, out_key::Vector{Int32}, in_key::Vector{Int32})
     base = 1 << basebit; n = length(out_key); Nk = length(in_key)
@@ -154,26 +257,35 @@ function keyswitch_key(rng, alpha, t::Int, basebit::Int, out_key::Vector{Int32},
         a = rand_uniform_torus32(rng, n)
         message = (in_key[i] * Int32(h)) << (32 - j * basebit)                                           # keyswitch.jl:35
         ks[1:n, h, j, i] = a
-        ks[n + 1, h, j, i] = message + dtot32(noise[h, j, i]) + reduce(+, a .* out_key)                  # lwe.jl:49-55
+        ks[n + 1, h, j, i] = message + dtot32(noise[h, j, i]) + wrapdot(a, out_key)                      # lwe.jl:49-55
     end
     ks
 end
 
-struct CloudKey                                                 # api.jl:111-127
+"""
+    CloudKey(rng, secret_key; device = 0, devices = nothing, flags = FLAG_SPLIT_FFT)
+
+api.jl:111-127.  `devices = :all` or a vector of GPU ordinals replicates the key on those GPUs; every gate call then
+shards its batch across them (tfhe_b200_multi_*).  The int32 coefficient form of the bootstrapping key is kept
+(the reference keeps only its transform, bootstrap.jl:12-14).
+"""
+struct CloudKey
     params::SchemeParameters
     ctx::Context
     bootstrap_key::Array{Int32}
     keyswitch_key::Array{Int32}
-    function CloudKey(rng::AbstractRNG, secret_key::SecretKey; device::Integer = 0, flags::UInt32 = FLAG_SPLIT_FFT)
+    function CloudKey(rng::AbstractRNG, secret_key::SecretKey; device::Integer = 0, devices = nothing, flags::UInt32 = FLAG_SPLIT_FFT)
         p = secret_key.params
-        ctx = Context(cparams(p, 1); device = device, flags = flags)
+        kctx = Context(cparams(p, 1); device = devices === nothing || devices === :all ? device : first(devices), flags = flags)
         tlwe_key = rand_uniform_bool(rng, p.tlwe_polynomial_degree, p.tlwe_mask_size)
-        bk = bootstrap_key(rng, ctx, p.bs_noise_stddev, secret_key.key, tlwe_key, p.bs_decomp_length, p.bs_log2_base)
+        bk = bootstrap_key(rng, kctx, p.bs_noise_stddev, secret_key.key, tlwe_key, p.bs_decomp_length, p.bs_log2_base)
         ks = keyswitch_key(rng, p.ks_noise_stddev, p.ks_decomp_length, p.ks_log2_base, secret_key.key, vec(tlwe_key))
+        ctx = devices === nothing ? kctx : Context(cparams(p, 1); devices = devices, flags = flags)
         load_bk!(ctx, bk); load_ksk!(ctx, ks)
         new(p, ctx, bk, ks)
     end
 end
+Base.Broadcast.broadcastable(ck::CloudKey) = (ck,)              # api.jl:130
 
 function make_key_pair(rng::AbstractRNG, params::Union{Nothing, SchemeParameters} = nothing; kwargs...)   # api.jl:139-146
     params === nothing && (params = tfhe_parameters_80())
@@ -183,43 +295,84 @@ end
 
 function lwe_encrypt(rng, message::Torus32, alpha::Float64, key::Vector{Int32})                           # lwe.jl:38-43
     a = rand_uniform_torus32(rng, length(key))
-    vcat(a, message + dtot32(randn(rng) * alpha) + reduce(+, a .* key))
+    LweSample(LweParams(length(key)), a, message + dtot32(randn(rng) * alpha) + wrapdot(a, key), alpha^2)
 end
 
-"api.jl:155-158; `message` may be a Bool or a vector of Bools (batched: one ciphertext per column)."
+"api.jl:155-158"
 encrypt(rng::AbstractRNG, key::SecretKey, message::Bool) =
-    LweSample(lwe_encrypt(rng, encode_message(message ? 1 : -1, 8), key.params.lwe_noise_stddev, key.key), key.params.lwe_noise_stddev^2)
-encrypt(rng::AbstractRNG, key::SecretKey, messages::AbstractVector{Bool}) =
-    LweSample(hcat([lwe_encrypt(rng, encode_message(m ? 1 : -1, 8), key.params.lwe_noise_stddev, key.key) for m in messages]...),
-              key.params.lwe_noise_stddev^2)
+    lwe_encrypt(rng, encode_message(message ? 1 : -1, 8), key.params.lwe_noise_stddev, key.key)
+"Batched form: one ciphertext per column of an `LweBatch`."
+encrypt(rng::AbstractRNG, key::SecretKey, messages::AbstractVector{Bool}) = LweBatch([encrypt(rng, key, m) for m in messages])
 
-lwe_phase(data::AbstractVector{Int32}, key) = data[end] - reduce(+, data[1:end-1] .* key)                 # lwe.jl:59
-decrypt(key::SecretKey, sample::LweSample) = ndims(sample.data) == 1 ? lwe_phase(sample.data, key.key) > 0 :
-    [lwe_phase(view(sample.data, :, g), key.key) > 0 for g in 1:size(sample.data, 2)]                     # api.jl:167-169
+lwe_phase(a::AbstractVector{Int32}, b::Int32, key) = b - wrapdot(a, key)                                   # lwe.jl:59
+decrypt(key::SecretKey, sample::LweSample) = lwe_phase(sample.a, sample.b, key.key) > 0                   # api.jl:167-169
+decrypt(key::SecretKey, batch::LweBatch) =
+    [lwe_phase(view(batch.data, 1:size(batch.data, 1) - 1, g), batch.data[end, g], key.key) > 0 for g in 1:length(batch)]
 
 # ---------------------------------------------------------------------------------------------- gates.jl
-as_batch(x::LweSample) = ndims(x.data) == 1 ? reshape(x.data, :, 1) : x.data
-function gate(ck, op::GateOp, xs::LweSample...)
-    mats = map(as_batch, xs)
-    out = c_gate(ck.ctx, op, mats[1], length(mats) > 1 ? mats[2] : nothing, length(mats) > 2 ? mats[3] : nothing, size(mats[1], 2))
-    LweSample(ndims(xs[1].data) == 1 ? vec(out) : out, 0.0)
+as_matrix(x::LweSample) = reshape(vcat(x.a, x.b), :, 1)
+as_matrix(x::LweBatch) = x.data
+as_matrix(x::AbstractVector{LweSample}) = LweBatch(x).data
+unpack(out::Matrix{Int32}, ::LweSample) = LweBatch(out, 0.0)[1]
+unpack(out::Matrix{Int32}, ::LweBatch) = LweBatch(out, 0.0)
+unpack(out::Matrix{Int32}, ::AbstractVector{LweSample}) = collect(LweBatch(out, 0.0))
+
+"One library call for the whole batch, whatever form the operands have (a sample, an `LweBatch`, a vector of samples)."
+function gate(ck::CloudKey, op::GateOp, xs...)
+    mats = map(as_matrix, xs)
+    count = size(mats[1], 2)
+    all(m -> size(m, 2) == count, mats) || throw(DimensionMismatch("gate operands hold different numbers of ciphertexts"))
+    out = c_gate(ck.ctx, op, mats[1], length(mats) > 1 ? mats[2] : nothing, length(mats) > 2 ? mats[3] : nothing, count)
+    unpack(out, xs[1])
 end
-gate_nand(ck, x, y) = gate(ck, NAND, x, y)          # gates.jl:15-18
-gate_or(ck, x, y) = gate(ck, OR, x, y)              # gates.jl:27-30
-gate_and(ck, x, y) = gate(ck, AND, x, y)            # gates.jl:39-42
-gate_xor(ck, x, y) = gate(ck, XOR, x, y)            # gates.jl:51-54
-gate_xnor(ck, x, y) = gate(ck, XNOR, x, y)          # gates.jl:63-66
-gate_not(ck, x) = gate(ck, NOT, x)                  # gates.jl:76-79
-gate_nor(ck, x, y) = gate(ck, NOR, x, y)            # gates.jl:102-105
-gate_andny(ck, x, y) = gate(ck, ANDNY, x, y)        # gates.jl:114-117
-gate_andyn(ck, x, y) = gate(ck, ANDYN, x, y)        # gates.jl:126-129
-gate_orny(ck, x, y) = gate(ck, ORNY, x, y)          # gates.jl:138-141
-gate_oryn(ck, x, y) = gate(ck, ORYN, x, y)          # gates.jl:150-153
-gate_mux(ck, x, y, z) = gate(ck, MUX, x, y, z)      # gates.jl:163-177
-function gate_constant(ck::CloudKey, value::Bool)   # gates.jl:91-93
+gate_nand(ck::CloudKey, x, y) = gate(ck, NAND, x, y)          # gates.jl:15-18
+gate_or(ck::CloudKey, x, y) = gate(ck, OR, x, y)              # gates.jl:27-30
+gate_and(ck::CloudKey, x, y) = gate(ck, AND, x, y)            # gates.jl:39-42
+gate_xor(ck::CloudKey, x, y) = gate(ck, XOR, x, y)            # gates.jl:51-54
+gate_xnor(ck::CloudKey, x, y) = gate(ck, XNOR, x, y)          # gates.jl:63-66
+gate_not(ck::CloudKey, x) = gate(ck, NOT, x)                  # gates.jl:76-79
+gate_nor(ck::CloudKey, x, y) = gate(ck, NOR, x, y)            # gates.jl:102-105
+gate_andny(ck::CloudKey, x, y) = gate(ck, ANDNY, x, y)        # gates.jl:114-117
+gate_andyn(ck::CloudKey, x, y) = gate(ck, ANDYN, x, y)        # gates.jl:126-129
+gate_orny(ck::CloudKey, x, y) = gate(ck, ORNY, x, y)          # gates.jl:138-141
+gate_oryn(ck::CloudKey, x, y) = gate(ck, ORYN, x, y)          # gates.jl:150-153
+gate_mux(ck::CloudKey, x, y, z) = gate(ck, MUX, x, y, z)      # gates.jl:163-177
+function gate_constant(ck::CloudKey, value::Bool)             # gates.jl:91-93
     flags = zeros(Int32, ck.params.lwe_size + 1, 1); flags[1, 1] = value
-    LweSample(vec(c_gate(ck.ctx, CONSTANT, flags, nothing, nothing, 1)), 0.0)
+    LweBatch(c_gate(ck.ctx, CONSTANT, flags, nothing, nothing, 1), 0.0)[1]
 end
+
+# Broadcasting.  `gate_xor.(cloud_key, xs, ys)` over vectors of samples lowers to
+# `materialize(broadcasted(gate_xor, cloud_key, xs, ys))`; these methods return the finished Vector{LweSample}
+# (materialize of an Array is the identity), computed as ONE batch instead of element by element.  Scalars mixed with
+# vectors (a single sample against a vector) are repeated to the common length, as broadcasting would do.
+const SampleVec = AbstractVector{LweSample}
+repeat_to(x::LweSample, count::Int) = repeat(as_matrix(x), 1, count)
+repeat_to(x::SampleVec, count::Int) = (length(x) == count || throw(DimensionMismatch("broadcast over ciphertext vectors of different lengths")); as_matrix(x))
+function broadcast_gate(ck::CloudKey, op::GateOp, xs...)
+    count = maximum(x isa LweSample ? 1 : length(x) for x in xs)
+    mats = map(x -> repeat_to(x, count), xs)
+    out = c_gate(ck.ctx, op, mats[1], length(mats) > 1 ? mats[2] : nothing, length(mats) > 2 ? mats[3] : nothing, count)
+    collect(LweBatch(out, 0.0))
+end
+for (f, op) in ((:gate_nand, NAND), (:gate_or, OR), (:gate_and, AND), (:gate_xor, XOR), (:gate_xnor, XNOR), (:gate_nor, NOR),
+                (:gate_andny, ANDNY), (:gate_andyn, ANDYN), (:gate_orny, ORNY), (:gate_oryn, ORYN))
+    @eval begin
+        Base.Broadcast.broadcasted(::typeof($f), ck::CloudKey, x::SampleVec, y::SampleVec) = broadcast_gate(ck, $op, x, y)
+        Base.Broadcast.broadcasted(::typeof($f), ck::CloudKey, x::LweSample, y::SampleVec) = broadcast_gate(ck, $op, x, y)
+        Base.Broadcast.broadcasted(::typeof($f), ck::CloudKey, x::SampleVec, y::LweSample) = broadcast_gate(ck, $op, x, y)
+    end
+end
+Base.Broadcast.broadcasted(::typeof(gate_not), ck::CloudKey, x::SampleVec) = broadcast_gate(ck, NOT, x)
+Base.Broadcast.broadcasted(::typeof(gate_mux), ck::CloudKey, x::Union{LweSample, SampleVec}, y::Union{LweSample, SampleVec},
+                           z::SampleVec) = broadcast_gate(ck, MUX, x, y, z)
+Base.Broadcast.broadcasted(::typeof(gate_mux), ck::CloudKey, x::SampleVec, y::Union{LweSample, SampleVec}, z::LweSample) =
+    broadcast_gate(ck, MUX, x, y, z)
+Base.Broadcast.broadcasted(::typeof(gate_mux), ck::CloudKey, x::LweSample, y::SampleVec, z::LweSample) = broadcast_gate(ck, MUX, x, y, z)
+# encrypt.(Ref(rng), secret_key, bits) and decrypt.(secret_key, samples): vectorised on the host in one pass
+Base.Broadcast.broadcasted(::typeof(encrypt), rng::Base.RefValue{<:AbstractRNG}, key::SecretKey, bits::AbstractVector{Bool}) =
+    [encrypt(rng[], key, m) for m in bits]
+Base.Broadcast.broadcasted(::typeof(decrypt), key::SecretKey, xs::SampleVec) = decrypt(key, LweBatch(xs))
 
 # ---------------------------------------------------------------------------------------------- multi-key
 "mk_internals.jl:6-18: `data` is (p*n+1) or (p*n+1, count): a[:, party] blocks then the joint b."
@@ -228,6 +381,7 @@ struct MKLweSample
     parties::Int
     current_variance::Float64
 end
+Base.Broadcast.broadcastable(x::MKLweSample) = (x,)
 
 struct SharedKey                                                # mk_internals.jl:101-112, mk_api.jl:44-50
     params::SchemeParameters
@@ -274,7 +428,7 @@ struct CloudKeyPart                                             # mk_api.jl:61-7
 end
 
 function decompose(x::Array{Int32}, l::Int, bgbit::Int)         # tgsw.jl:99-117 (host side, key expansion only)
-    offset = signed(UInt32(sum(Int64(1) << (32 - r * bgbit) for r in 1:l) * (1 << (bgbit - 1)) % 2^32))
+    offset = reinterpret(Int32, UInt32((sum(Int64(1) << (32 - r * bgbit) for r in 1:l) * (1 << (bgbit - 1))) % 2^32))
     [((x .+ offset) .>> (32 - r * bgbit)) .& Int32((1 << bgbit) - 1) .- Int32(1 << (bgbit - 1)) for r in 1:l]
 end
 
@@ -282,7 +436,7 @@ struct MKCloudKey                                               # mk_api.jl:85-1
     parties::Int
     params::SchemeParameters
     ctx::Context
-    function MKCloudKey(ck_parts::Vector{CloudKeyPart}; flags::UInt32 = FLAG_SPLIT_FFT)
+    function MKCloudKey(ck_parts::Vector{CloudKeyPart}; devices = nothing, flags::UInt32 = FLAG_SPLIT_FFT)
         params = ck_parts[1].params; p = length(ck_parts)
         @assert p <= params.max_parties                                                                  # mk_api.jl:94
         kctx = mk_keygen_ctx(params, ck_parts[1].device)
@@ -311,35 +465,63 @@ struct MKCloudKey                                               # mk_api.jl:85-1
             bk[:, (2l * p + 1):(2l * p + l), :, i] = ue[:c0]
             bk[:, (2l * p + l + 1):(2l * p + 2l), :, i] = ue[:c1]
         end
-        ctx = Context(cparams(params, p); device = ck_parts[1].device, flags = flags)
+        ctx = devices === nothing ? Context(cparams(params, p); device = ck_parts[1].device, flags = flags) :
+                                    Context(cparams(params, p); devices = devices, flags = flags)
         load_bk!(ctx, bk)
         load_ksk!(ctx, cat([part.ks for part in ck_parts]..., dims = 5))
         new(p, params, ctx)
     end
 end
+Base.Broadcast.broadcastable(ck::MKCloudKey) = (ck,)
 
 function mk_encrypt(rng, secret_keys::Vector{SecretKey}, message::Bool)                                   # mk_api.jl:110-126
     params = secret_keys[1].params
     keys = vcat([sk.key for sk in secret_keys]...)
     a = rand_uniform_torus32(rng, length(keys))
-    b = encode_message(message ? 1 : -1, 8) + dtot32(randn(rng) * params.lwe_noise_stddev) + reduce(+, a .* keys)
+    b = encode_message(message ? 1 : -1, 8) + dtot32(randn(rng) * params.lwe_noise_stddev) + wrapdot(a, keys)
     MKLweSample(vcat(a, b), length(secret_keys), params.lwe_noise_stddev^2)
 end
 mk_encrypt(rng, secret_keys::Vector{SecretKey}, messages::AbstractVector{Bool}) =
     MKLweSample(hcat([mk_encrypt(rng, secret_keys, m).data for m in messages]...), length(secret_keys), secret_keys[1].params.lwe_noise_stddev^2)
 
+mk_phase(data::AbstractVector{Int32}, keys) = data[end] - wrapdot(view(data, 1:length(data) - 1), keys)
 function mk_decrypt(secret_keys::Vector{SecretKey}, sample::MKLweSample)                                  # mk_api.jl:135-138
     keys = vcat([sk.key for sk in secret_keys]...)
-    ndims(sample.data) == 1 ? lwe_phase(sample.data, keys) > 0 : [lwe_phase(view(sample.data, :, g), keys) > 0 for g in 1:size(sample.data, 2)]
+    ndims(sample.data) == 1 ? mk_phase(sample.data, keys) > 0 : [mk_phase(view(sample.data, :, g), keys) > 0 for g in 1:size(sample.data, 2)]
 end
 
+mk_matrix(x::MKLweSample) = ndims(x.data) == 1 ? reshape(x.data, :, 1) : x.data
+
 function mk_gate_nand(ck::MKCloudKey, x::MKLweSample, y::MKLweSample)                                      # mk_gates.jl:7-12
-    xm = ndims(x.data) == 1 ? reshape(x.data, :, 1) : x.data
-    ym = ndims(y.data) == 1 ? reshape(y.data, :, 1) : y.data
+    xm = mk_matrix(x); ym = mk_matrix(y)
     out = similar(xm)
-    GC.@preserve xm ym out check(ck.ctx, ccall((:tfhe_b200_mk_nand_batch, LIB), Cint,
-        (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Csize_t), ck.ctx.handle, xm, ym, out, size(xm, 2)))
+    GC.@preserve xm ym out begin
+        rc = if ck.ctx.multi
+            ccall((:tfhe_b200_multi_mk_nand_batch, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Csize_t),
+                  ck.ctx.handle, pointer(xm), pointer(ym), pointer(out), size(xm, 2))
+        else
+            ccall((:tfhe_b200_mk_nand_batch, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Csize_t),
+                  ck.ctx.handle, pointer(xm), pointer(ym), pointer(out), size(xm, 2))
+        end
+        check(ck.ctx, rc)
+    end
     MKLweSample(ndims(x.data) == 1 ? vec(out) : out, ck.parties, 0.0)
+end
+
+"mk_bootstrap (mk_internals.jl:512-515) with an arbitrary test-vector value `mu`"
+mk_bootstrap(ck::MKCloudKey, mu::Torus32, x::MKLweSample) =
+    (out = c_bootstrap(ck.ctx, mu, mk_matrix(x)); MKLweSample(ndims(x.data) == 1 ? vec(out) : out, ck.parties, 0.0))
+
+"bootstrap (bootstrap.jl:92-95) with an arbitrary test-vector value `mu`"
+bootstrap(ck::CloudKey, mu::Torus32, x::Union{LweSample, LweBatch}) = unpack(c_bootstrap(ck.ctx, mu, as_matrix(x)), x)
+
+# mk_gate_nand.(ck, xs, ys) over vectors of single MK samples: one call
+function Base.Broadcast.broadcasted(::typeof(mk_gate_nand), ck::MKCloudKey, xs::AbstractVector{MKLweSample}, ys::AbstractVector{MKLweSample})
+    length(xs) == length(ys) || throw(DimensionMismatch("broadcast over ciphertext vectors of different lengths"))
+    x = MKLweSample(hcat((vec(s.data) for s in xs)...), ck.parties, 0.0)
+    y = MKLweSample(hcat((vec(s.data) for s in ys)...), ck.parties, 0.0)
+    out = mk_gate_nand(ck, x, y)
+    [MKLweSample(out.data[:, g], ck.parties, 0.0) for g in 1:size(out.data, 2)]
 end
 
 end # module
