@@ -164,6 +164,40 @@ int tfhe_b200_mk_keyswitch_batch(tfhe_b200_ctx* ctx, const int32_t* in, int32_t*
 int tfhe_b200_mk_extern_product_batch(tfhe_b200_ctx* ctx, const int32_t* acc, const int32_t* party,
                                       const int32_t* bk_index, int32_t* out, size_t count);
 
+/* ---- the steps either side of the path on the device ---------------------- */
+/* Every function here that consumes randomness exists in two forms: *_words takes the random words from the caller
+ * (so a CPU oracle fed the same words must produce the same bits), the other generates them on the device with a
+ * counter-based generator (Philox4x32-10; mask words = stream 1 of `seed`, Gaussian noise = Box-Muller over stream 2)
+ * and never moves them through the host.  key_len is n for single-key and p*n for MK ciphertexts.  k = 1 only. */
+/* word i of Philox stream (seed, stream), i < count (tests, reproducibility) */
+int tfhe_b200_random_words(tfhe_b200_ctx* ctx, uint64_t seed, uint64_t stream, int32_t* out, size_t count);
+/* lwe_encrypt (lwe.jl:38-55): out[g] = (a[g], mu[g] + noise[g] + <a[g], key>); a [count][key_len], out [count][key_len+1] */
+int tfhe_b200_lwe_encrypt_words_batch(tfhe_b200_ctx* ctx, const int32_t* key, int32_t key_len, const int32_t* mu,
+                                      const int32_t* noise, const int32_t* a, int32_t* out, size_t count);
+/* encrypt (api.jl:155-158) / mk_encrypt (mk_api.jl:110-126) of count bits (bytes, 0 or 1) with noise stddev sigma */
+int tfhe_b200_encrypt_batch(tfhe_b200_ctx* ctx, const int32_t* key, int32_t key_len, const uint8_t* bits, double sigma,
+                            uint64_t seed, int32_t* out, size_t count);
+/* the same with the ciphertexts left in HBM (out_dev is a DEVICE pointer; key and bits are host pointers) */
+int tfhe_b200_encrypt_batch_dev(tfhe_b200_ctx* ctx, const int32_t* key, int32_t key_len, const uint8_t* bits, double sigma,
+                                uint64_t seed, int32_t* out_dev, size_t count, void* stream);
+/* lwe_phase (lwe.jl:59) and decrypt (api.jl:167-169, mk_api.jl:135-138): phase[g] = b - <a, key>, bits_out[g] = phase > 0;
+ * either output may be NULL */
+int tfhe_b200_lwe_phase_batch(tfhe_b200_ctx* ctx, const int32_t* key, int32_t key_len, const int32_t* ct, int32_t* phase,
+                              uint8_t* bits_out, size_t count);
+/* BootstrapKey (bootstrap.jl:6-15; tgsw_encrypt tgsw.jl:84-88, tlwe_encrypt_zero tlwe.jl:63-73) generated, transformed
+ * and loaded on the device: lwe_key [n], tlwe_key [N], a / noise [n*l*2][N] (sample (i, r, j): mask polynomial and
+ * noise polynomial).  bk_out (nullable) receives the coefficient form [n][l][2][2][N]. */
+int tfhe_b200_keygen_bk_words(tfhe_b200_ctx* ctx, const int32_t* lwe_key, const int32_t* tlwe_key, const int32_t* a,
+                              const int32_t* noise, int32_t* bk_out);
+int tfhe_b200_keygen_bk(tfhe_b200_ctx* ctx, const int32_t* lwe_key, const int32_t* tlwe_key, double sigma, uint64_t seed,
+                        int32_t* bk_out);
+/* KeyswitchKey (keyswitch.jl:14-41) generated and loaded on the device: out_key [n], in_key [N*k], a [N*k][t][base-1][n],
+ * noise [N*k][t][base-1] (already centred, keyswitch.jl:29).  ksk_out (nullable) receives [N*k][t][base-1][n+1]. */
+int tfhe_b200_keygen_ksk_words(tfhe_b200_ctx* ctx, const int32_t* out_key, const int32_t* in_key, const int32_t* a,
+                               const int32_t* noise, int32_t* ksk_out);
+int tfhe_b200_keygen_ksk(tfhe_b200_ctx* ctx, const int32_t* out_key, const int32_t* in_key, double sigma, uint64_t seed,
+                         int32_t* ksk_out);
+
 /* ---- one logical context over several GPUs ------------------------------------ */
 /* Gates are independent (gates.jl:15-18) and the evaluation keys are read-only, so a batch shards across GPUs with
  * no exchange step: keys are replicated at load, every call cuts its batch into contiguous shards of whole CTA

@@ -13,12 +13,13 @@ C_TYPES = {
     "const char*": "cstr", "double*": "ptr_f64", "const int32_t*": "ptr_i32", "int32_t*": "ptr_i32", "const int*": "ptr_i32",
     "tfhe_b200_ctx*": "ptr_void", "const tfhe_b200_ctx*": "ptr_void", "tfhe_b200_multi*": "ptr_void",
     "const tfhe_b200_multi*": "ptr_void", "void*": "ptr_void", "tfhe_b200_ctx**": "ptr_ptr", "tfhe_b200_multi**": "ptr_ptr",
-    "const tfhe_b200_params*": "ptr_params",
+    "const tfhe_b200_params*": "ptr_params", "const uint8_t*": "ptr_u8", "uint8_t*": "ptr_u8", "double": "f64",
 }
 JL_TYPES = {
     "Cint": "i32", "Cvoid": "void", "Csize_t": "usize", "UInt32": "u32", "Int32": "i32", "UInt64": "u64", "Cstring": "cstr",
     "Ptr{Int32}": "ptr_i32", "Ptr{Cint}": "ptr_i32", "Ptr{Cvoid}": "ptr_void", "Ref{Ptr{Cvoid}}": "ptr_ptr",
     "Ref{CParams}": "ptr_params", "Ptr{Float64}": "ptr_f64", "Ref{Float64}": "ptr_f64", "Ref{Cdouble}": "ptr_f64",
+    "Ptr{UInt8}": "ptr_u8", "Cdouble": "f64", "Float64": "f64",
 }
 
 

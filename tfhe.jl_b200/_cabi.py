@@ -83,6 +83,15 @@ def lib():
             "tfhe_b200_mk_extern_product_batch": (C.c_int, [vp, i32p, i32p, i32p, i32p, sz]),
             "tfhe_b200_mk_bootstrap_batch": (C.c_int, [vp, C.c_int32, i32p, i32p, sz]),
             "tfhe_b200_mk_bootstrap_batch_dev": (C.c_int, [vp, C.c_int32, i32p, i32p, sz, vp]),
+            "tfhe_b200_random_words": (C.c_int, [vp, C.c_uint64, C.c_uint64, i32p, sz]),
+            "tfhe_b200_lwe_encrypt_words_batch": (C.c_int, [vp, i32p, C.c_int32, i32p, i32p, i32p, i32p, sz]),
+            "tfhe_b200_encrypt_batch": (C.c_int, [vp, i32p, C.c_int32, vp, C.c_double, C.c_uint64, i32p, sz]),
+            "tfhe_b200_encrypt_batch_dev": (C.c_int, [vp, i32p, C.c_int32, vp, C.c_double, C.c_uint64, i32p, sz, vp]),
+            "tfhe_b200_lwe_phase_batch": (C.c_int, [vp, i32p, C.c_int32, i32p, i32p, vp, sz]),
+            "tfhe_b200_keygen_bk_words": (C.c_int, [vp, i32p, i32p, i32p, i32p, i32p]),
+            "tfhe_b200_keygen_bk": (C.c_int, [vp, i32p, i32p, C.c_double, C.c_uint64, i32p]),
+            "tfhe_b200_keygen_ksk_words": (C.c_int, [vp, i32p, i32p, i32p, i32p, i32p]),
+            "tfhe_b200_keygen_ksk": (C.c_int, [vp, i32p, i32p, C.c_double, C.c_uint64, i32p]),
             "tfhe_b200_multi_create": (C.c_int, [C.POINTER(CParams), C.POINTER(C.c_int), C.c_int, C.c_uint32, C.POINTER(vp)]),
             "tfhe_b200_multi_destroy": (None, [vp]),
             "tfhe_b200_multi_last_error": (C.c_char_p, [vp]),
@@ -262,6 +271,72 @@ class Context:
         x = np.atleast_2d(_host(x)); y = np.atleast_2d(_host(y)); out = np.empty_like(x)
         assert x.shape == y.shape and x.shape[1] == self.ct_words
         self._ck(lib().tfhe_b200_mk_nand_batch(self._h, _addr(x), _addr(y), _addr(out), x.shape[0]))
+        return out
+
+    # ---- the steps either side of the path, on the device
+    def random_words(self, seed, stream, count):
+        out = np.empty(count, dtype=np.int32)
+        self._ck(lib().tfhe_b200_random_words(self._h, seed, stream, _addr(out), count))
+        return out
+
+    def lwe_encrypt_words(self, key, mu, noise, a):
+        key = _host(key); a = np.atleast_2d(_host(a)); mu = _host(mu).reshape(-1); noise = _host(noise).reshape(-1)
+        count = a.shape[0]
+        assert a.shape[1] == key.size and mu.size == count and noise.size == count
+        out = np.empty((count, key.size + 1), dtype=np.int32)
+        self._ck(lib().tfhe_b200_lwe_encrypt_words_batch(self._h, _addr(key), key.size, _addr(mu), _addr(noise), _addr(a), _addr(out), count))
+        return out
+
+    def encrypt(self, key, bits, sigma, seed):
+        """encrypt (api.jl:155-158) of an array of bits; mask and noise are generated on the device from `seed`."""
+        key = _host(key); bits = np.ascontiguousarray(np.asarray(bits, dtype=bool).reshape(-1), dtype=np.uint8)
+        out = np.empty((bits.size, key.size + 1), dtype=np.int32)
+        self._ck(lib().tfhe_b200_encrypt_batch(self._h, _addr(key), key.size, bits.ctypes.data, float(sigma), int(seed), _addr(out), bits.size))
+        return out
+
+    def encrypt_dev(self, key, bits, sigma, seed, out_ptr, stream=0):
+        key = _host(key); bits = np.ascontiguousarray(np.asarray(bits, dtype=bool).reshape(-1), dtype=np.uint8)
+        self._ck(lib().tfhe_b200_encrypt_batch_dev(self._h, _addr(key), key.size, bits.ctypes.data, float(sigma), int(seed), out_ptr,
+                                                   bits.size, stream or None))
+
+    def lwe_phase(self, key, ct):
+        key = _host(key); ct = np.atleast_2d(_host(ct))
+        assert ct.shape[1] == key.size + 1
+        phase = np.empty(ct.shape[0], dtype=np.int32)
+        self._ck(lib().tfhe_b200_lwe_phase_batch(self._h, _addr(key), key.size, _addr(ct), _addr(phase), None, ct.shape[0]))
+        return phase
+
+    def decrypt(self, key, ct):
+        key = _host(key); ct = np.atleast_2d(_host(ct))
+        assert ct.shape[1] == key.size + 1
+        bits = np.empty(ct.shape[0], dtype=np.uint8)
+        self._ck(lib().tfhe_b200_lwe_phase_batch(self._h, _addr(key), key.size, _addr(ct), None, bits.ctypes.data, ct.shape[0]))
+        return bits.astype(bool)
+
+    def keygen_bk(self, lwe_key, tlwe_key, sigma=None, seed=None, a=None, noise=None, keep=True):
+        """Generates, transforms and loads the bootstrapping key on the device; returns its int32 coefficient form
+        ([n][l][2][2][N]) when `keep`.  Either (sigma, seed) or explicit randomness (a, noise: [n*l*2][N])."""
+        lwe_key = _host(lwe_key, (self.n,)); tlwe_key = _host(tlwe_key).reshape(-1)
+        assert tlwe_key.size == self.N and self.k == 1
+        out = np.empty((self.n, self.l, 2, 2, self.N), dtype=np.int32) if keep else None
+        if a is not None:
+            a = _host(a, (self.n * self.l * 2, self.N)); noise = _host(noise, (self.n * self.l * 2, self.N))
+            self._ck(lib().tfhe_b200_keygen_bk_words(self._h, _addr(lwe_key), _addr(tlwe_key), _addr(a), _addr(noise), _addr(out)))
+        else:
+            self._ck(lib().tfhe_b200_keygen_bk(self._h, _addr(lwe_key), _addr(tlwe_key), float(sigma), int(seed), _addr(out)))
+        return out
+
+    def keygen_ksk(self, out_key, in_key, sigma=None, seed=None, a=None, noise=None, keep=True):
+        """Generates and loads the key-switching key on the device; returns [N*k][t][base-1][n+1] when `keep`."""
+        out_key = _host(out_key, (self.n,)); in_key = _host(in_key).reshape(-1)
+        base1 = (1 << self.basebit) - 1
+        assert in_key.size == self.N * self.k
+        out = np.empty((self.N * self.k, self.t, base1, self.n + 1), dtype=np.int32) if keep else None
+        if a is not None:
+            a = _host(a, (self.N * self.k, self.t, base1, self.n)); noise = _host(noise, (self.N * self.k, self.t, base1))
+            self._ck(lib().tfhe_b200_keygen_ksk_words(self._h, _addr(out_key), _addr(in_key), _addr(a), _addr(noise), _addr(out)))
+        else:
+            self._ck(lib().tfhe_b200_keygen_ksk(self._h, _addr(out_key), _addr(in_key), float(sigma), int(seed), _addr(out)))
         return out
 
     # ---- device buffers (raw addresses, e.g. torch ``tensor.data_ptr()``); asynchronous on ``stream``

@@ -198,12 +198,22 @@ class CloudKey:                               # api.jl:111-127
     """Evaluation key.  Key material is generated on the host and loaded onto `device`; the int32
     coefficient form of the bootstrap key is kept (the reference keeps only its transform)."""
 
-    def __init__(self, rng, secret_key: SecretKey, device: int = 0, flags: int = _cabi.FLAG_SPLIT_FFT, devices=None):
+    def __init__(self, rng, secret_key: SecretKey, device: int = 0, flags: int = _cabi.FLAG_SPLIT_FFT, devices=None,
+                 device_keygen: bool = False):
         """``devices``: a list of GPU ordinals or ``"all"`` — the key is then replicated on every listed GPU and each
-        gate batch is sharded across them (one ``gate_nand(ck, x, y)`` uses every GPU)."""
+        gate batch is sharded across them (one ``gate_nand(ck, x, y)`` uses every GPU).
+        ``device_keygen``: every random word of the key (24 576 LWE and 2 000 TLWE encryptions at the 80-bit set) is
+        generated on the GPU from one seed drawn from ``rng`` (tfhe_b200_keygen_bk / _ksk) instead of in numpy."""
         p = secret_key.params
         self.params = p
         self.mctx = None
+        if device_keygen and devices is None and p.tlwe_mask_size == 1:
+            self.ctx = _context(p, 1, device, flags)
+            tlwe_key = rand_uniform_bool(rng, p.tlwe_mask_size, p.tlwe_polynomial_degree)
+            seed = int(rng.integers(0, 2 ** 63))
+            self.bootstrap_key = self.ctx.keygen_bk(secret_key.key, tlwe_key, sigma=p.bs_noise_stddev, seed=seed)
+            self.keyswitch_key = self.ctx.keygen_ksk(secret_key.key, tlwe_key.reshape(-1), sigma=p.ks_noise_stddev, seed=seed)
+            return
         if devices is not None:
             self.mctx = _cabi.MultiContext(n=p.lwe_size, N=p.tlwe_polynomial_degree, k=p.tlwe_mask_size, l=p.bs_decomp_length,
                                            bgbit=p.bs_log2_base, t=p.ks_decomp_length, basebit=p.ks_log2_base, parties=1,
@@ -230,15 +240,22 @@ def make_key_pair(rng, params: Optional[SchemeParameters] = None, device: int = 
     return secret_key, CloudKey(rng, secret_key, device=device, flags=flags, devices=devices)
 
 
-def encrypt(rng, key: SecretKey, message) -> LweSample:
-    """api.jl:155-158; `message` may be a bool or an array of bools (batched)."""
+def encrypt(rng, key: SecretKey, message, ctx: Optional[Context] = None) -> LweSample:
+    """api.jl:155-158; `message` may be a bool or an array of bools (batched).  With a device context (`ctx`, e.g.
+    ``cloud_key.ctx``) the mask and the noise are generated on the GPU from one seed drawn from `rng`."""
     m = np.asarray(message, dtype=bool)
+    if ctx is not None:
+        out = ctx.encrypt(key.key, m.reshape(-1), key.params.lwe_noise_stddev, int(rng.integers(0, 2 ** 63)))
+        return LweSample(out.reshape(m.shape + (key.key.size + 1,)), key.params.lwe_noise_stddev ** 2)
     mu = np.where(m, encode_message(1, 8), encode_message(-1, 8))
     return lwe_encrypt(rng, mu, key.params.lwe_noise_stddev, key.key)
 
 
-def decrypt(key: SecretKey, sample: LweSample):
-    """api.jl:167-169"""
+def decrypt(key: SecretKey, sample: LweSample, ctx: Optional[Context] = None):
+    """api.jl:167-169 (on the GPU when a device context is given)"""
+    if ctx is not None:
+        r = ctx.decrypt(key.key, sample.data.reshape(-1, key.key.size + 1)).reshape(sample.data.shape[:-1])
+        return bool(r) if np.ndim(r) == 0 else r
     r = lwe_phase(sample, key.key) > 0
     return bool(r) if np.ndim(r) == 0 else r
 

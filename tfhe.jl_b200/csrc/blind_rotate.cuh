@@ -117,12 +117,22 @@ template <int L, int NP, int STAGES, int ORDER = 0, int PROBE = 0, int LA_ = 0, 
         iss++;
         if (++iss_stage == STAGES) { iss_stage = 0; iss_round++; }
         if (++iss_q == kChunksPerIter) { iss_q = 0; iss_i++; }
-        if (DIST) { if (++turn == nwarps) turn = 0; }
+        if (DIST == 1) { if (++turn == nwarps) turn = 0; }
     }
     __device__ __forceinline__ void prologue() {
+        if (DIST == 2) return;                // the dedicated producer warp runs produce_all()
         while (iss < LA && iss < total) {
             if (producer && (!DIST || turn == warp)) issue_now();
             if (!DIST && !producer) break;   // only the producer thread keeps a cursor
+            advance();
+        }
+    }
+    // DIST == 2: the whole walk, by one thread of a warp that does nothing else — it runs as far ahead of the consumers
+    // as the ring is deep and only ever waits for a stage to drain, never for data it needs itself
+    __device__ __forceinline__ void produce_all() {
+        while (iss < total) {
+            if (iss_round >= 1) mbar_wait(empty + iss_stage, (uint32_t)(iss_round - 1) & 1u);
+            issue_now();
             advance();
         }
     }
@@ -133,7 +143,7 @@ template <int L, int NP, int STAGES, int ORDER = 0, int PROBE = 0, int LA_ = 0, 
         return done;
     }
     __device__ __forceinline__ const double2* acquire(int first_of_pass /*consumption order is fixed*/) {
-        if (DIST) {
+        if (DIST == 1) {
             if (iss < total) {   // iss == k + LA: CTA-uniform
                 if (producer && turn == warp) {
                     long long c0 = 0;
@@ -529,9 +539,14 @@ __host__ __device__ constexpr int br_tmem_cols(int NP, int G, int L = 2, int TM 
 // (SYNC == 2 transforms, no X2 buffer: room for a deeper ring); bit 3 = clock64 phase probe (development; writes
 // A.probe); bit 2 = ring refills issued by the warps in turn + early barrier test; bits 4-6 = look-ahead of the
 // ring producer in chunks (0 = STAGES - 1)
+// bit 7 = a dedicated producer warp walks the ring and the compute warps only consume.  The CTA then has a third
+// warpgroup (384 threads are launched with 168 registers each); it hands its registers back (setmaxnreg.dec 24) and the
+// two compute warpgroups grow to 240 (setmaxnreg.inc), so every sub-partition holds 240 + 240 + 24 registers per lane —
+// the full file — and no compute warp executes producer code or waits for a stage to drain.
 template <int L, int BGBIT, int NP, int G, int STAGES, int MODE, int TM = 0, int OPT = 0>
-__global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs A) {
-    constexpr int PROBE = (OPT >> 3) & 1, POLL = OPT & 1, SYNCM = (OPT & 2) ? 2 : 1, LA = (OPT >> 4) & 7, DIST = (OPT >> 2) & 1;
+__global__ void __launch_bounds__(64 * G + ((OPT >> 7) & 1) * 128, 1) blind_rotate_kernel(BlindRotateArgs A) {
+    constexpr int PROBE = (OPT >> 3) & 1, POLL = OPT & 1, SYNCM = (OPT & 2) ? 2 : 1, LA = (OPT >> 4) & 7;
+    constexpr int PWARP = (OPT >> 7) & 1, DIST = PWARP ? 2 : (OPT >> 2) & 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t s_tmem_base;
     // TM: 0 = accumulators in registers, 1 = all in TMEM, 2 = component 1 in TMEM,
@@ -564,6 +579,15 @@ __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs
     BkFromRing<L, NP, STAGES, TM == 3 ? 1 : 0, PROBE, LA, POLL, DIST> bk{ring, full, empty, A.bk_fft, A.n_iter * 2 * L * NP, 0, 0, 0u,
                                                                             DIST ? (threadIdx.x & 31) == 0 : threadIdx.x == 0};
     if (DIST) { bk.warp = threadIdx.x >> 5; bk.nwarps = 2 * G; }
+    if (PWARP) {
+        static_assert(!PWARP || G == 4, "register rebalancing assumes two full compute warpgroups");
+        if ((threadIdx.x >> 5) >= 2 * G) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 24;" ::: "memory");
+            if (threadIdx.x == 64 * G) bk.produce_all();
+            return;   // the compute warps meet at named barriers only from here on
+        }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 240;" ::: "memory");
+    }
     bk.prologue();   // the first STAGES-1 chunks are in flight while the gate prologue below runs
 
     // ---------------- consumers: one 64-thread group per gate ----------------
@@ -640,7 +664,8 @@ __global__ void __launch_bounds__(64 * G, 1) blind_rotate_kernel(BlindRotateArgs
     }
     if (kUseTmem) {
         tmem_fence_before_sync();
-        __syncthreads();
+        if (PWARP) asm volatile("bar.sync 15, %0;" ::"n"(64 * G) : "memory");   // the producer warp has left
+        else __syncthreads();
         if ((threadIdx.x >> 5) == 0) tmem_dealloc<kTmemCols>(s_tmem_base);
     }
 }

@@ -20,6 +20,7 @@
 #include "mk_kernels.cuh"
 #include "mk_blind_rotate.cuh"
 #include "mk_blind_rotate_lowlat.cuh"
+#include "keygen.cuh"
 
 using namespace tfhe_b200;
 
@@ -118,7 +119,7 @@ int launch_br_g(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
     if (smem > 227 * 1024) return fail(ctx, TFHE_B200_EINVAL, "LWE dimension too large for the shared-memory layout");
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned grid = (unsigned)((A.count + G - 1) / G);
-    kern<<<grid, 64 * G, smem, s>>>(A);
+    kern<<<grid, 64 * G + ((OPT >> 7) & 1) * 128, smem, s>>>(A);
     CU(cudaGetLastError());
     ctx->launches++;
     return 0;
@@ -145,13 +146,15 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
             case 344: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 2 | (4 << 4)>(ctx, A, s); else break; // look-ahead 4, try_wait
             case 354: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 4>(ctx, A, s); else break;            // refills by the warps in turn + early test
             case 364: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 6 | (5 << 4)>(ctx, A, s); else break; // + in-place exchange, 7 stages, look-ahead 5
-            case 1304:                                                                  // clock64 phase probe of 304 / 1334: of 354
+            case 374: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 128 | 2>(ctx, A, s); else break;      // dedicated producer warp, in-place exchange, 7 stages
+            case 384: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 128>(ctx, A, s); else break;          // dedicated producer warp, 5 stages
+            case 1304:                                                                  // clock64 phase probe of 304 / 1334: of 374
             case 1334:
                 if constexpr (NP == 2 && L == 2 && MODE == 0) {
                     BlindRotateArgs B = A;
                     CU(cudaMalloc(&B.probe, 4 * 8 * 8 * sizeof(unsigned long long)));
                     int rc = ctx->G == 1304 ? launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 8>(ctx, B, s)
-                                            : launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 8 | 4>(ctx, B, s);
+                                            : launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 8 | 128 | 2>(ctx, B, s);
                     std::vector<unsigned long long> h(4 * 8 * 8);
                     CU(cudaStreamSynchronize(s));
                     CU(cudaMemcpy(h.data(), B.probe, h.size() * 8, cudaMemcpyDeviceToHost));
@@ -701,6 +704,7 @@ int tfhe_b200_polymul_batch(tfhe_b200_ctx* ctx, const int32_t* x, const int32_t*
 }
 
 #include "mk_cabi.inc"
+#include "keygen_cabi.inc"
 
 // ---- measurement helper -------------------------------------------------------------------------------
 int tfhe_b200_measure_fp64_tflops(tfhe_b200_ctx* ctx, double* out_tflops) {
