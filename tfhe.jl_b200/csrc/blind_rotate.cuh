@@ -154,7 +154,7 @@ template <int L, int NP, int STAGES, int ORDER = 0, int PROBE = 0, int LA_ = 0, 
                 }
                 advance();
             }
-        } else if (producer && iss < total) {
+        } else if (DIST == 0 && producer && iss < total) {
             long long c0 = 0;
             if (PROBE) c0 = clock64();
             // the stage's previous occupant (chunk iss - STAGES) must have been released by every warp
@@ -539,6 +539,7 @@ __host__ __device__ constexpr int br_tmem_cols(int NP, int G, int L = 2, int TM 
 // (SYNC == 2 transforms, no X2 buffer: room for a deeper ring); bit 3 = clock64 phase probe (development; writes
 // A.probe); bit 2 = ring refills issued by the warps in turn + early barrier test; bits 4-6 = look-ahead of the
 // ring producer in chunks (0 = STAGES - 1)
+// bits 8-9 = start-up stagger of groups 2, 3 in units of 2 500 cycles (0 = none)
 // bit 7 = a dedicated producer warp walks the ring and the compute warps only consume.  The CTA then has a third
 // warpgroup (384 threads are launched with 168 registers each); it hands its registers back (setmaxnreg.dec 24) and the
 // two compute warpgroups grow to 240 (setmaxnreg.inc), so every sub-partition holds 240 + 240 + 24 registers per lane —
@@ -638,6 +639,14 @@ __global__ void __launch_bounds__(64 * G + ((OPT >> 7) & 1) * 128, 1) blind_rota
     long long pr[4] = {0, 0, 0, 0};
     long long t_start = 0;
     if (PROBE) t_start = clock64();
+    if constexpr (((OPT >> 8) & 3) != 0) {
+        // Start-up stagger: the groups of the second warpgroup begin about one multiply-accumulate pass later, so that
+        // their shared-memory-bound pass overlaps transforms of the first two groups instead of their passes.
+        if (grp & 2) {
+            const long long until = clock64() + 2500LL * ((OPT >> 8) & 3);
+            while (clock64() < until) {}
+        }
+    }
 #pragma unroll 1
     for (int i = 0; i < A.n_iter; i++) {   // bootstrap.jl:19-23
         if constexpr (TM == 3) extern_product_step_os<L, BGBIT, SYNCM, PROBE>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id, pr);

@@ -148,6 +148,9 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
             case 364: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 6 | (5 << 4)>(ctx, A, s); else break; // + in-place exchange, 7 stages, look-ahead 5
             case 374: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 128 | 2>(ctx, A, s); else break;      // dedicated producer warp, in-place exchange, 7 stages
             case 384: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 128>(ctx, A, s); else break;          // dedicated producer warp, 5 stages
+            case 394: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 128 | 2 | (1 << 8)>(ctx, A, s); else break;   // 374 + stagger 2 500 cycles
+            case 404: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 128 | 2 | (2 << 8)>(ctx, A, s); else break;   // 374 + stagger 5 000 cycles
+            case 414: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 128 | (1 << 8)>(ctx, A, s); else break;       // 384 + stagger 2 500 cycles
             case 1304:                                                                  // clock64 phase probe of 304 / 1334: of 374
             case 1334:
                 if constexpr (NP == 2 && L == 2 && MODE == 0) {
