@@ -151,6 +151,7 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
             case 394: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 128 | 2 | (1 << 8)>(ctx, A, s); else break;   // 374 + stagger 2 500 cycles
             case 404: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 128 | 2 | (2 << 8)>(ctx, A, s); else break;   // 374 + stagger 5 000 cycles
             case 414: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 128 | (1 << 8)>(ctx, A, s); else break;       // 384 + stagger 2 500 cycles
+            case 484: if constexpr (NP == 1) return launch_br_g<L, BGBIT, NP, 4, 6, MODE, 0, 128>(ctx, A, s); else break;          // one piece, register accumulators + producer warpgroup
             case 1304:                                                                  // clock64 phase probe of 304 / 1334: of 374
             case 1334:
                 if constexpr (NP == 2 && L == 2 && MODE == 0) {
@@ -194,7 +195,9 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
                     }
                     if (A.count <= sms) return launch_br_g<L, BGBIT, NP, 1, 6, MODE, TMv>(ctx, A, s);
                     if (A.count <= 2 * sms) return launch_br_g<L, BGBIT, NP, 2, 6, MODE, TMv>(ctx, A, s);
-                    return launch_br_g<L, BGBIT, NP, 4, 6, MODE, TMv>(ctx, A, s);
+                    // two pieces: output-stationary step + dedicated producer warpgroup (profiles/r2: 486 vs 563 ms per 65 536 gates)
+                    if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 128>(ctx, A, s);
+                    else return launch_br_g<L, BGBIT, NP, 4, 6, MODE, TMv>(ctx, A, s);
                 }
         }
         return launch_br_g<L, BGBIT, NP, 4, 6, MODE>(ctx, A, s);   // a two-piece-only variant was asked for with one piece
