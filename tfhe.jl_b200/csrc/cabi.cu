@@ -45,6 +45,7 @@ struct tfhe_b200_ctx {
     int lowlat = 1;                  // batches of <= 1 gate per SM: one gate per CTA spread over 4 groups + sliced key switch
     int ks_tile = 1;                 // large batches: tiled key switch (TFHE_B200_KS_TILE=0: one CTA per ciphertext)
     int mk_ring = 1;                 // MK blind rotation: 1 = TMA key ring, several gates per CTA (mk_blind_rotate.cuh)
+    int mk_pw = 1;                   // MK ring kernel: dedicated producer warpgroup (TFHE_B200_MK_PW=0: in-line producer)
     cudaStream_t stream = nullptr;   // used by the host-buffer entry points
     double2* d_E = nullptr;          // exp(-i*pi*x/1024), x < 2048
     double2* d_bk_fft = nullptr;     // single-key: [n][l][2][2][NP][512]; MK: [p][n][l*(2p+2)][NP][512]
@@ -197,7 +198,7 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
                     if (A.count <= 2 * sms) return launch_br_g<L, BGBIT, NP, 2, 6, MODE, TMv>(ctx, A, s);
                     // two pieces: output-stationary step + dedicated producer warpgroup (profiles/r2: 486 vs 563 ms per 65 536 gates)
                     if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 128>(ctx, A, s);
-                    else return launch_br_g<L, BGBIT, NP, 4, 6, MODE, TMv>(ctx, A, s);
+                    else return launch_br_g<L, BGBIT, NP, 4, 6, MODE, 0, 128>(ctx, A, s);   // one piece: register accumulators + producer warpgroup
                 }
         }
         return launch_br_g<L, BGBIT, NP, 4, 6, MODE>(ctx, A, s);   // a two-piece-only variant was asked for with one piece
@@ -397,6 +398,7 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
     c->NP = (flags & TFHE_B200_FLAG_UNSPLIT_FFT) ? 1 : 2;
     c->G = env_int("TFHE_B200_G", 0);
     c->mk_ring = env_int("TFHE_B200_MK_RING", 1);
+    c->mk_pw = env_int("TFHE_B200_MK_PW", 1);
     c->lowlat = env_int("TFHE_B200_LOWLAT", 1);
     c->ks_tile = env_int("TFHE_B200_KS_TILE", 1);
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) c->sm_count = prop.multiProcessorCount; }

@@ -25,7 +25,7 @@
 namespace tfhe_b200 {
 
 // ring of whole key polynomials (all NP pieces): NP * 8 KB per stage
-template <int NP, int STAGES> struct MkKeyRing {
+template <int NP, int STAGES, int PW = 0> struct MkKeyRing {
     static constexpr int kElems = NP * kSpectrum;
     static constexpr uint32_t kBytes = (uint32_t)kElems * 16u;
     const double2* ring; uint64_t* full; uint64_t* empty;
@@ -50,10 +50,27 @@ template <int NP, int STAGES> struct MkKeyRing {
         }
     }
     __device__ __forceinline__ void prologue() {
-        if (producer)
+        if (producer && !PW)
             while (iss < STAGES - 1 && iss < total) issue_next();
     }
+    // PW: the whole walk by one thread of a warp that does nothing else (see blind_rotate.cuh, BkFromRing DIST == 2)
+    __device__ __forceinline__ void produce_all() {
+        while (iss < total) {
+            if (iss_round >= 1) mbar_wait(empty + iss_stage, (uint32_t)(iss_round - 1) & 1u);
+            issue_next();
+        }
+    }
+    uint32_t ready_next = 0;   // PW: early test of the next polynomial's barrier (an mbarrier test costs 100-150 cycles)
     __device__ __forceinline__ const double2* acquire() {
+        if (PW) {
+            if (!ready_next) mbar_wait_poll(full + stage, phase);
+            const int ns = stage + 1 == STAGES ? 0 : stage + 1;
+            uint32_t done;
+            asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(smem_u32(full + ns)), "r"(ns == 0 ? phase ^ 1u : phase) : "memory");
+            ready_next = done;
+            return ring + (size_t)stage * kElems;
+        }
         if (producer && iss < total) {
             // refill the stage released one chunk ago (all groups passed it an FFT ago)
             if (iss_round >= 1) mbar_wait(empty + iss_stage, (uint32_t)(iss_round - 1) & 1u);
@@ -184,11 +201,14 @@ __host__ __device__ constexpr int mk_tmem_cols(int NP, int G) {
     return c;
 }
 
-template <int L, int BGBIT, int NP, int G, int STAGES>
-__global__ void __launch_bounds__(64 * G, 1) mk_blind_rotate_ring_kernel(MKBlindRotateArgs M) {
+// PW: a dedicated producer warpgroup walks the key ring (see blind_rotate.cuh, OPT bit 7).  With G = 4 the CTA is launched
+// with 384 threads at 168 registers and rebalanced to 240 / 24 by setmaxnreg; with G = 2 (256 threads, 255 registers) the
+// sub-partitions hold one compute and one producer warp each and nothing needs rebalancing.
+template <int L, int BGBIT, int NP, int G, int STAGES, int PW = 0>
+__global__ void __launch_bounds__(64 * G + PW * 128, 1) mk_blind_rotate_ring_kernel(MKBlindRotateArgs M) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t s_tmem_base;
-    using Ring = MkKeyRing<NP, STAGES>;
+    using Ring = MkKeyRing<NP, STAGES, PW>;
     const int p = M.p, n = M.n;
     const int cpi = mk_chunks_per_iter(L, p);
     if ((threadIdx.x >> 5) == 0) tmem_alloc<mk_tmem_cols(NP, G)>(&s_tmem_base);
@@ -225,6 +245,14 @@ __global__ void __launch_bounds__(64 * G, 1) mk_blind_rotate_ring_kernel(MKBlind
     const uint32_t tmS = s_tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * mk_tmem_cols_per_warp(NP));
 
     Ring key{ring, full, empty, M.bk_fft, order, cpi, n, L * (2 * p + 2), p * n * cpi, threadIdx.x == 0};
+    if (PW) {
+        if ((threadIdx.x >> 5) >= 2 * G) {
+            if (G == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;" ::: "memory");
+            if (threadIdx.x == 64 * G) key.produce_all();
+            return;   // the compute warps meet at named barriers only from here on
+        }
+        if (G == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 240;" ::: "memory");
+    }
     key.prologue();
 
     const int t = threadIdx.x & 63, grp = threadIdx.x >> 6;
@@ -276,7 +304,8 @@ __global__ void __launch_bounds__(64 * G, 1) mk_blind_rotate_ring_kernel(MKBlind
         if (t == 0) o[p * kN] = acc[p * kN];
     }
     tmem_fence_before_sync();
-    __syncthreads();
+    if (PW) asm volatile("bar.sync 15, %0;" ::"n"(64 * G) : "memory");   // the producer warpgroup has left
+    else __syncthreads();
     if ((threadIdx.x >> 5) == 0) tmem_dealloc<mk_tmem_cols(NP, G)>(s_tmem_base);
 }
 
