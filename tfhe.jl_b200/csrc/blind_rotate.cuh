@@ -75,31 +75,26 @@ constexpr int kChunkBytes = kChunkElems * 16;     // 16 KB
 // sub-partition and cap every thread at 168 registers (16K registers per sub-partition).
 // ORDER == 0: chunks are consumed in the order (c, r, half); ORDER == 1 (two-piece transforms, output-stationary
 // step): (c', c, r) — all digit polynomials against the two pieces of output component c' = 0, then c' = 1.
-// LA = look-ahead in chunks (0: STAGES - 1, the deepest the ring allows; then the producer refills the stage released
-// one chunk ago and has to wait for the slowest group; with LA < STAGES - 1 the stage it refills was released
-// STAGES - 1 - LA chunks earlier).  POLL: consumers poll the full barrier instead of the suspending try_wait.
-// DIST: the refills are issued by the warps in turn (lane 0 of warp j % NW issues the j-th refill) instead of by
-// thread 0 alone, and every consumer tests the NEXT chunk's barrier one chunk early.  Measured with the clock64 probe
-// (DESIGN.md): an mbarrier test costs 100-150 cycles even when the phase is long complete; with one producer thread
-// that latency (twice per chunk: empty + full) plus the issue code made warp 0 the straggler of the CTA (8.2 k cycles
-// in the multiply-accumulate phase against 5.9 k for its sibling warp) and every other group waited for it.
-template <int L, int NP, int STAGES, int ORDER = 0, int PROBE = 0, int LA_ = 0, int POLL = 0, int DIST = 0> struct BkFromRing {
+//
+// PW == 0: thread 0 of the CTA is also the producer: just before it waits for chunk k it refills the stage that chunk
+//          k-1 occupied with chunk k+STAGES-1.
+// PW == 1: a dedicated warp walks the ring (produce_all) and the compute warps only consume; every consumer also tests
+//          the NEXT chunk's barrier one chunk early.  Measured with the clock64 probe: an mbarrier test
+//          costs 100-150 cycles even when the phase is long complete; with the in-line producer that latency (twice per
+//          chunk: empty + full) plus the issue code made warp 0 the straggler of the CTA (8.2 k cycles in the
+//          multiply-accumulate phase against 5.9 k for its sibling warp) and every other group waited for it.
+template <int L, int NP, int STAGES, int ORDER = 0, int PROBE = 0, int PW = 0> struct BkFromRing {
     static constexpr int kChunksPerIter = 2 * L * NP;
-    static constexpr int LA = LA_ ? LA_ : STAGES - 1;
-    static_assert(LA >= 1 && LA <= STAGES - 1, "look-ahead must leave one stage to the consumers");
     const double2* ring; uint64_t* full; uint64_t* empty;
     const double2* bk;        // start of the key, [n_iter][kChunksPerIter] chunks
     int total;                // chunks in the whole walk
-    int k;                    // sequence number of the next chunk to consume
     int stage; uint32_t phase;
-    bool producer;            // DIST == 0: thread 0 of the CTA;  DIST == 1: lane 0 of every warp
+    bool producer;            // PW == 0: thread 0 of the CTA
     long long w_full = 0, w_empty = 0, w_first = 0;   // PROBE: cycles spent waiting (all chunks / producer / first chunk of a pass)
     // producer cursor: the next chunk to issue (sequence number, its stage, how often that stage has been used, its
-    // position (iteration, index in the iteration)) — advanced incrementally, no division in the loop.  With DIST every
-    // thread advances the cursor (the values are CTA-uniform) and `turn` names the warp whose lane 0 issues.
+    // position (iteration, index in the iteration)) — advanced incrementally, no division in the loop
     int iss = 0, iss_stage = 0, iss_round = 0, iss_i = 0, iss_q = 0;
-    int turn = 0, warp = 0, nwarps = 1;
-    uint32_t ready_next = 0;  // DIST: result of the early test of the next chunk's full barrier
+    uint32_t ready_next = 0;  // PW: result of the early test of the next chunk's full barrier
 
     // index in the iteration (consumption order) -> chunk inside the stored row: storage order is (r, c, half)
     static __device__ __forceinline__ int stored_index(int q) {
@@ -108,32 +103,24 @@ template <int L, int NP, int STAGES, int ORDER = 0, int PROBE = 0, int LA_ = 0, 
         const int r = cr % L, c = cr / L;
         return (r * 2 + c) * NP + h;
     }
-    __device__ __forceinline__ void issue_now() {
+    __device__ __forceinline__ void issue_next() {
         const size_t off = ((size_t)iss_i * kChunksPerIter + (size_t)stored_index(iss_q)) * kChunkElems;
         mbar_arrive_expect_tx(full + iss_stage, kChunkBytes);
         bulk_copy_g2s(const_cast<double2*>(ring) + (size_t)iss_stage * kChunkElems, bk + off, kChunkBytes, full + iss_stage);
-    }
-    __device__ __forceinline__ void advance() {
         iss++;
         if (++iss_stage == STAGES) { iss_stage = 0; iss_round++; }
         if (++iss_q == kChunksPerIter) { iss_q = 0; iss_i++; }
-        if (DIST == 1) { if (++turn == nwarps) turn = 0; }
     }
     __device__ __forceinline__ void prologue() {
-        if (DIST == 2) return;                // the dedicated producer warp runs produce_all()
-        while (iss < LA && iss < total) {
-            if (producer && (!DIST || turn == warp)) issue_now();
-            if (!DIST && !producer) break;   // only the producer thread keeps a cursor
-            advance();
-        }
+        if (!PW && producer)
+            while (iss < STAGES - 1 && iss < total) issue_next();
     }
-    // DIST == 2: the whole walk, by one thread of a warp that does nothing else — it runs as far ahead of the consumers
-    // as the ring is deep and only ever waits for a stage to drain, never for data it needs itself
+    // PW: the whole walk, by one thread of a warp that does nothing else — it runs as far ahead of the consumers as the
+    // ring is deep and only ever waits for a stage to drain, never for data it needs itself
     __device__ __forceinline__ void produce_all() {
         while (iss < total) {
             if (iss_round >= 1) mbar_wait(empty + iss_stage, (uint32_t)(iss_round - 1) & 1u);
-            issue_now();
-            advance();
+            issue_next();
         }
     }
     static __device__ __forceinline__ uint32_t test(uint64_t* bar, uint32_t parity) {
@@ -143,41 +130,30 @@ template <int L, int NP, int STAGES, int ORDER = 0, int PROBE = 0, int LA_ = 0, 
         return done;
     }
     __device__ __forceinline__ const double2* acquire(int first_of_pass /*consumption order is fixed*/) {
-        if (DIST == 1) {
-            if (iss < total) {   // iss == k + LA: CTA-uniform
-                if (producer && turn == warp) {
-                    long long c0 = 0;
-                    if (PROBE) c0 = clock64();
-                    if (iss_round >= 1) mbar_wait(empty + iss_stage, (uint32_t)(iss_round - 1) & 1u);
-                    if (PROBE) w_empty += clock64() - c0;
-                    issue_now();
-                }
-                advance();
-            }
-        } else if (DIST == 0 && producer && iss < total) {
+        if (!PW && producer && iss < total) {
             long long c0 = 0;
             if (PROBE) c0 = clock64();
             // the stage's previous occupant (chunk iss - STAGES) must have been released by every warp
             if (iss_round >= 1) mbar_wait(empty + iss_stage, (uint32_t)(iss_round - 1) & 1u);
             if (PROBE) w_empty += clock64() - c0;
-            issue_now();
-            advance();
+            issue_next();
         }
         long long c1 = 0;
         if (PROBE) c1 = clock64();
-        if (DIST) {
+        if (PW) {
             if (!ready_next) mbar_wait_poll(full + stage, phase);
             // test the following chunk now; the answer is back long before the next acquire needs it
             const int ns = stage + 1 == STAGES ? 0 : stage + 1;
             ready_next = test(full + ns, ns == 0 ? phase ^ 1u : phase);
-        } else if (POLL) mbar_wait_poll(full + stage, phase); else mbar_wait(full + stage, phase);
+        } else {
+            mbar_wait(full + stage, phase);
+        }
         if (PROBE) { const long long d = clock64() - c1; w_full += d; if (first_of_pass) w_first += d; }
         return ring + (size_t)stage * kChunkElems;
     }
     __device__ __forceinline__ void release() {
         __syncwarp();
         if ((threadIdx.x & 31) == 0) mbar_arrive(empty + stage);
-        k++;
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
     static __device__ __forceinline__ double2 load(const double2* p) { return *p; }
@@ -517,13 +493,12 @@ struct BlindRotateArgs {
 
 // per-group shared memory: X1 + X2 + acc (+ bara, n_pad words)
 __host__ __device__ constexpr int group_smem_bytes(int /*NP*/) { return (kSpectrum + kX2Elems) * 16 + 2 * kN * 4; }
-// TM == 3 (output-stationary step): two X1 buffers per group, used alternately (SYNC == 1 transforms); with OPT bit 1
-// (SYNC == 2 transforms) the second exchange happens in place and there is no X2 buffer
-__host__ __device__ constexpr size_t br_group_bytes(int NP, int TM, int OPT) {
-    return TM == 3 ? (size_t)2 * kSpectrum * 16 + ((OPT & 2) ? 0 : kX2Elems * 16) + 2 * kN * 4 : (size_t)group_smem_bytes(NP);
+// TM == 3 (output-stationary step): two X1 buffers per group, used alternately (SYNC == 1 transforms)
+__host__ __device__ constexpr size_t br_group_bytes(int NP, int TM) {
+    return (size_t)group_smem_bytes(NP) + (TM == 3 ? kSpectrum * 16 : 0);
 }
-__host__ __device__ constexpr size_t br_smem_bytes(int NP, int G, int STAGES, int n_pad, int TM = 0, int OPT = 0) {
-    return (size_t)STAGES * kChunkBytes + 128 + (size_t)G * (br_group_bytes(NP, TM, OPT) + n_pad * 4);
+__host__ __device__ constexpr size_t br_smem_bytes(int NP, int G, int STAGES, int n_pad, int TM = 0) {
+    return (size_t)STAGES * kChunkBytes + 128 + (size_t)G * (br_group_bytes(NP, TM) + n_pad * 4);
 }
 
 // TMEM columns to allocate when the accumulators live in tensor memory: warps that share a lane quarter
@@ -535,19 +510,15 @@ __host__ __device__ constexpr int br_tmem_cols(int NP, int G, int L = 2, int TM 
     return c;
 }
 
-// OPT (TM == 3 only): bit 0 = consumers poll the key ring (no suspending try_wait); bit 1 = in-place second exchange
-// (SYNC == 2 transforms, no X2 buffer: room for a deeper ring); bit 3 = clock64 phase probe (development; writes
-// A.probe); bit 2 = ring refills issued by the warps in turn + early barrier test; bits 4-6 = look-ahead of the
-// ring producer in chunks (0 = STAGES - 1)
-// bits 8-9 = start-up stagger of groups 2, 3 in units of 2 500 cycles (0 = none)
-// bit 7 = a dedicated producer warp walks the ring and the compute warps only consume.  The CTA then has a third
-// warpgroup (384 threads are launched with 168 registers each); it hands its registers back (setmaxnreg.dec 24) and the
-// two compute warpgroups grow to 240 (setmaxnreg.inc), so every sub-partition holds 240 + 240 + 24 registers per lane —
-// the full file — and no compute warp executes producer code or waits for a stage to drain.
+// OPT: bit 3 = clock64 phase probe (development; TM == 3 only; writes A.probe);
+//      bit 7 = a dedicated producer warp walks the key ring and the compute warps only consume.  The CTA then has a
+//      third warpgroup (384 threads are launched with 168 registers each); it hands its registers back
+//      (setmaxnreg.dec 24) and the two compute warpgroups grow to 240 (setmaxnreg.inc), so every sub-partition holds
+//      240 + 240 + 24 registers per lane — the full file — and no compute warp executes producer code or waits for a
+//      stage to drain.
 template <int L, int BGBIT, int NP, int G, int STAGES, int MODE, int TM = 0, int OPT = 0>
 __global__ void __launch_bounds__(64 * G + ((OPT >> 7) & 1) * 128, 1) blind_rotate_kernel(BlindRotateArgs A) {
-    constexpr int PROBE = (OPT >> 3) & 1, POLL = OPT & 1, SYNCM = (OPT & 2) ? 2 : 1, LA = (OPT >> 4) & 7;
-    constexpr int PWARP = (OPT >> 7) & 1, DIST = PWARP ? 2 : (OPT >> 2) & 1;
+    constexpr int PROBE = (OPT >> 3) & 1, PWARP = (OPT >> 7) & 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t s_tmem_base;
     // TM: 0 = accumulators in registers, 1 = all in TMEM, 2 = component 1 in TMEM,
@@ -556,7 +527,7 @@ __global__ void __launch_bounds__(64 * G + ((OPT >> 7) & 1) * 128, 1) blind_rota
     static_assert(TM != 3 || NP == 2, "the output-stationary step is the two-piece path");
     constexpr int kTmemCols = br_tmem_cols(NP, G, L, TM);
     static_assert(kTmemCols <= 512, "tensor memory: too many gates per CTA");
-    constexpr size_t kGroupBytes = br_group_bytes(NP, TM, OPT);
+    constexpr size_t kGroupBytes = br_group_bytes(NP, TM);
     if (kUseTmem) {
         if ((threadIdx.x >> 5) == 0) tmem_alloc<kTmemCols>(&s_tmem_base);
         tmem_fence_before_sync();
@@ -577,9 +548,7 @@ __global__ void __launch_bounds__(64 * G + ((OPT >> 7) & 1) * 128, 1) blind_rota
         const int warp = threadIdx.x >> 5;
         tm = s_tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * br_tmem_cols_per_warp(NP, L, TM));
     }
-    BkFromRing<L, NP, STAGES, TM == 3 ? 1 : 0, PROBE, LA, POLL, DIST> bk{ring, full, empty, A.bk_fft, A.n_iter * 2 * L * NP, 0, 0, 0u,
-                                                                            DIST ? (threadIdx.x & 31) == 0 : threadIdx.x == 0};
-    if (DIST) { bk.warp = threadIdx.x >> 5; bk.nwarps = 2 * G; }
+    BkFromRing<L, NP, STAGES, TM == 3 ? 1 : 0, PROBE, PWARP> bk{ring, full, empty, A.bk_fft, A.n_iter * 2 * L * NP, 0, 0u, threadIdx.x == 0};
     if (PWARP) {
         static_assert(!PWARP || G == 4, "register rebalancing assumes two full compute warpgroups");
         if ((threadIdx.x >> 5) >= 2 * G) {
@@ -596,8 +565,8 @@ __global__ void __launch_bounds__(64 * G + ((OPT >> 7) & 1) * 128, 1) blind_rota
     const int bar_id = grp + 1;
     unsigned char* base = groups + (size_t)grp * (kGroupBytes + A.n_pad * 4);
     double2* X1 = reinterpret_cast<double2*>(base);                      // TM == 3: two buffers, used alternately
-    double2* X2 = X1 + (TM == 3 ? 2 : 1) * kSpectrum;                   // TM == 3 with OPT bit 1: unused (in-place exchange)
-    int32_t* acc = reinterpret_cast<int32_t*>(X2 + ((TM == 3 && (OPT & 2)) ? 0 : kX2Elems));
+    double2* X2 = X1 + (TM == 3 ? 2 : 1) * kSpectrum;
+    int32_t* acc = reinterpret_cast<int32_t*>(X2 + kX2Elems);
     int32_t* bara = acc + 2 * kN;
     const unsigned long long g = (unsigned long long)blockIdx.x * G + grp;
     const bool valid = g < A.count;   // a group without a gate still walks the ring (on zeros) to keep the lockstep
@@ -639,17 +608,9 @@ __global__ void __launch_bounds__(64 * G + ((OPT >> 7) & 1) * 128, 1) blind_rota
     long long pr[4] = {0, 0, 0, 0};
     long long t_start = 0;
     if (PROBE) t_start = clock64();
-    if constexpr (((OPT >> 8) & 3) != 0) {
-        // Start-up stagger: the groups of the second warpgroup begin about one multiply-accumulate pass later, so that
-        // their shared-memory-bound pass overlaps transforms of the first two groups instead of their passes.
-        if (grp & 2) {
-            const long long until = clock64() + 2500LL * ((OPT >> 8) & 3);
-            while (clock64() < until) {}
-        }
-    }
 #pragma unroll 1
     for (int i = 0; i < A.n_iter; i++) {   // bootstrap.jl:19-23
-        if constexpr (TM == 3) extern_product_step_os<L, BGBIT, SYNCM, PROBE>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id, pr);
+        if constexpr (TM == 3) extern_product_step_os<L, BGBIT, 1, PROBE>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id, pr);
         else if constexpr (TM != 0) extern_product_step_tmem<L, BGBIT, NP, (TM == 2 && NP == 2) ? 1 : 0>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id);
         else extern_product_step<L, BGBIT, NP, true, true>(acc, bara[i], bk, w, X1, X2, t, bar_id);
     }

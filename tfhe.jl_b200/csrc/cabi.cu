@@ -116,7 +116,7 @@ int env_int(const char* name, int dflt) {
 template <int L, int BGBIT, int NP, int G, int STAGES, int MODE, int TM = 0, int OPT = 0>
 int launch_br_g(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
     auto kern = blind_rotate_kernel<L, BGBIT, NP, G, STAGES, MODE, TM, OPT>;
-    const size_t smem = br_smem_bytes(NP, G, STAGES, A.n_pad, TM, OPT);
+    const size_t smem = br_smem_bytes(NP, G, STAGES, A.n_pad, TM);
     if (smem > 227 * 1024) return fail(ctx, TFHE_B200_EINVAL, "LWE dimension too large for the shared-memory layout");
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned grid = (unsigned)((A.count + G - 1) / G);
@@ -134,32 +134,16 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
     } else {
         // 4 gates = 8 warps = 2 per SM sub-partition: the only shape that leaves 255 registers per thread
         switch (ctx->G) {
-            case 104: return launch_br_g<L, BGBIT, NP, 4, 6, MODE, 1>(ctx, A, s);   // all accumulators in TMEM
-            case 106: return launch_br_g<L, BGBIT, NP, 6, 3, MODE, 1>(ctx, A, s);
-            case 204: return launch_br_g<L, BGBIT, NP, 4, 6, MODE, 2>(ctx, A, s);   // component 0 in registers, component 1 in TMEM
-            case 4: return launch_br_g<L, BGBIT, NP, 4, 6, MODE>(ctx, A, s);           // register accumulators
-            case 304:                                                                   // output-stationary step (two pieces only)
+            // development knobs (A/B runs): the round-1 kernel, the output-stationary step without the producer warpgroup
+            case 204: return launch_br_g<L, BGBIT, NP, 4, 6, MODE, NP == 2 ? 2 : 0>(ctx, A, s);
+            case 304:
                 if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3>(ctx, A, s);
                 else return launch_br_g<L, BGBIT, NP, 4, 6, MODE>(ctx, A, s);
-            case 314: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 1>(ctx, A, s); else break;            // + polling
-            case 324: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 2>(ctx, A, s); else break;            // in-place exchange, 7 stages
-            case 334: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 3 | (4 << 4)>(ctx, A, s); else break; // + polling, look-ahead 4
-            case 344: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 2 | (4 << 4)>(ctx, A, s); else break; // look-ahead 4, try_wait
-            case 354: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 4>(ctx, A, s); else break;            // refills by the warps in turn + early test
-            case 364: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 6 | (5 << 4)>(ctx, A, s); else break; // + in-place exchange, 7 stages, look-ahead 5
-            case 374: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 128 | 2>(ctx, A, s); else break;      // dedicated producer warp, in-place exchange, 7 stages
-            case 384: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 128>(ctx, A, s); else break;          // dedicated producer warp, 5 stages
-            case 394: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 128 | 2 | (1 << 8)>(ctx, A, s); else break;   // 374 + stagger 2 500 cycles
-            case 404: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 128 | 2 | (2 << 8)>(ctx, A, s); else break;   // 374 + stagger 5 000 cycles
-            case 414: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 128 | (1 << 8)>(ctx, A, s); else break;       // 384 + stagger 2 500 cycles
-            case 484: if constexpr (NP == 1) return launch_br_g<L, BGBIT, NP, 4, 6, MODE, 0, 128>(ctx, A, s); else break;          // one piece, register accumulators + producer warpgroup
-            case 1304:                                                                  // clock64 phase probe of 304 / 1334: of 374
-            case 1334:
+            case 1304:                                                                  // clock64 phase probe of the default kernel
                 if constexpr (NP == 2 && L == 2 && MODE == 0) {
                     BlindRotateArgs B = A;
                     CU(cudaMalloc(&B.probe, 4 * 8 * 8 * sizeof(unsigned long long)));
-                    int rc = ctx->G == 1304 ? launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 8>(ctx, B, s)
-                                            : launch_br_g<L, BGBIT, NP, 4, 7, MODE, 3, 8 | 128 | 2>(ctx, B, s);
+                    int rc = launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 8 | 128>(ctx, B, s);
                     std::vector<unsigned long long> h(4 * 8 * 8);
                     CU(cudaStreamSynchronize(s));
                     CU(cudaMemcpy(h.data(), B.probe, h.size() * 8, cudaMemcpyDeviceToHost));
@@ -173,9 +157,6 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
                     return rc;
                 } else return launch_br_g<L, BGBIT, NP, 4, 6, MODE>(ctx, A, s);
             default:
-                // measured (profiles/r1): with one 32-bit piece the 64 accumulator registers fit and registers win
-                // (148 k vs 135 k gates/s); with two pieces (128 registers) the fastest is component 0 in registers
-                // and component 1 in TMEM (102 k; all in TMEM 98 k; all in registers, 72 B of spills, 88 k gates/s)
                 // Small batches (dependent circuits, single gates): fewer gates per CTA so that every gate gets an
                 // SM (sub-partition) of its own — a lone group finishes an iteration ~3x sooner than four sharing
                 // the FP64 pipe, and groups without a gate would only burn cycles on zeros.

@@ -152,8 +152,8 @@ struct NoPrefetch { __device__ __forceinline__ void operator()() const {} };
 //            passed the barrier of transform k may already store pass-1 results of transform k+1 while the other warp
 //            of the group still loads X1 of transform k; it cannot reach transform k+2 before that warp has arrived at
 //            the barrier of transform k+1, i.e. has consumed those loads).
-// SYNC == 2: as SYNC == 1, and the second exchange happens in place inside the tile's own 1 KB block of X1 (X2 is not
-//            used at all): 8 KB less shared memory per gate, which the key ring gets.
+// (An in-place variant of the second exchange — XOR-swizzled inside the tile's own 1 KB block of X1, no X2 buffer,
+// two more ring stages — was bit-exact and 2 % slower: profiles/r2/k3_variants.md.)
 template <int SYNC, class W, class F>
 __device__ __forceinline__ void fft512_forward_t(double2 (&a)[8], const W& w, double2* X1, double2* X2, int t,
                                                  int bar_id, F&& prefetch) {
@@ -179,29 +179,13 @@ __device__ __forceinline__ void fft512_forward_t(double2 (&a)[8], const W& w, do
 #pragma unroll
         for (int q = 1; q < 8; q++) a[q] = cmul(a[q], V[q]);
     }
-    if (SYNC == 2) {
-        // Tile hi has just read exactly block hi of X1 (64 entries, 1 KB) and nobody else reads that block, so the tile
-        // transposes in place: entry (row r, column c) at r*8 + (c ^ r).  The XOR keeps every quarter-warp access on 8
-        // distinct 16-byte bank groups, and with the 1 KB-aligned block it is one LOP3 on the byte address.
-        char* blk = reinterpret_cast<char*>(X1 + hi * 64);
-        __syncwarp();
+    if (SYNC == 1) __syncwarp();   // the tile's loads of the previous transform's X2 are done
 #pragma unroll
-        for (int q2 = 0; q2 < 8; q2++)
-            *reinterpret_cast<double2*>(blk + ((uint32_t)(lo << 4) ^ (uint32_t)(q2 << 4)) + q2 * 128) = a[q2];
-        __syncwarp();
-        prefetch();
+    for (int q2 = 0; q2 < 8; q2++) X2[hi * 72 + q2 * 9 + lo] = a[q2];
+    if (SYNC == 1) __syncwarp(); else group_sync(bar_id);
+    prefetch();
 #pragma unroll
-        for (int t1 = 0; t1 < 8; t1++)
-            a[t1] = *reinterpret_cast<const double2*>(blk + ((uint32_t)(lo * 128 + (lo << 4)) ^ (uint32_t)(t1 << 4)));
-    } else {
-        if (SYNC == 1) __syncwarp();   // the tile's loads of the previous transform's X2 are done
-#pragma unroll
-        for (int q2 = 0; q2 < 8; q2++) X2[hi * 72 + q2 * 9 + lo] = a[q2];
-        if (SYNC == 1) __syncwarp(); else group_sync(bar_id);
-        prefetch();
-#pragma unroll
-        for (int t1 = 0; t1 < 8; t1++) a[t1] = X2[hi * 72 + lo * 9 + t1];
-    }
+    for (int t1 = 0; t1 < 8; t1++) a[t1] = X2[hi * 72 + lo * 9 + t1];
     dft8<false>(a);
 }
 template <class W, class F = NoPrefetch>
@@ -222,26 +206,13 @@ __device__ __forceinline__ void fft512_inverse_t(double2 (&a)[8], const W& w, do
 #pragma unroll
         for (int q = 1; q < 8; q++) a[q] = cmulc(a[q], V[q]);
     }
-    if (SYNC == 2) {
-        char* blk = reinterpret_cast<char*>(X1 + hi * 64);   // in-place tile transpose, see fft512_forward_t
-        __syncwarp();
+    if (SYNC == 1) __syncwarp();
 #pragma unroll
-        for (int t1 = 0; t1 < 8; t1++)
-            *reinterpret_cast<double2*>(blk + ((uint32_t)(lo * 128 + (lo << 4)) ^ (uint32_t)(t1 << 4))) = a[t1];
-        __syncwarp();
+    for (int t1 = 0; t1 < 8; t1++) X2[hi * 72 + lo * 9 + t1] = a[t1];
+    if (SYNC == 1) __syncwarp(); else group_sync(bar_id);
 #pragma unroll
-        for (int q2 = 0; q2 < 8; q2++)
-            a[q2] = *reinterpret_cast<const double2*>(blk + ((uint32_t)(lo << 4) ^ (uint32_t)(q2 << 4)) + q2 * 128);
-    } else {
-        if (SYNC == 1) __syncwarp();
-#pragma unroll
-        for (int t1 = 0; t1 < 8; t1++) X2[hi * 72 + lo * 9 + t1] = a[t1];
-        if (SYNC == 1) __syncwarp(); else group_sync(bar_id);
-#pragma unroll
-        for (int q2 = 0; q2 < 8; q2++) a[q2] = X2[hi * 72 + q2 * 9 + lo];
-    }
+    for (int q2 = 0; q2 < 8; q2++) a[q2] = X2[hi * 72 + q2 * 9 + lo];
     dft8<true>(a);   // q2 -> t2
-    if (SYNC == 2) __syncwarp();   // the tile is done reading its block before the block is overwritten
 #pragma unroll
     for (int t2 = 0; t2 < 8; t2++) X1[hi * 64 + lo + 8 * t2] = a[t2];
     group_sync(bar_id);
