@@ -325,8 +325,12 @@ def main():
                                        "note": "reference precision regime (polynomials.jl:138-140): one 32-bit piece, exact in every test, no proof"}
             uctx.close()
         if world > 1:
-            # ONE process driving all GPUs through the product's multi-device context; the other ranks stay idle
-            dist.barrier()
+            # ONE process driving all GPUs through the product's multi-device context; the other ranks stay idle.
+            # They must wait on the HOST: an NCCL barrier is a kernel spinning on their GPU, and kernels of two processes
+            # time-slice a GPU, which would halve the speed of rank 0's shard on that GPU.
+            host = dist.new_group(backend="gloo")
+            torch.cuda.synchronize()
+            dist.barrier(group=host)
             if rank == 0:
                 m = _cabi.MultiContext(n=P.n, l=P.l, bgbit=P.bgbit, t=P.t, basebit=P.basebit, devices=list(range(world)), flags=flags)
                 m.load_bk(keys.bk); m.load_ksk(keys.ksk)
@@ -343,7 +347,7 @@ def main():
                 extras["e2e_single_process"] = {"value": B * world * reps / sp, "unit": "gates/s", "devices": m.devices,
                                                 "note": "one process, tfhe_b200_multi_gate_batch: host buffers in, host buffer out, batch sharded over all GPUs"}
                 m.close()
-            dist.barrier()
+            dist.barrier(group=host)
 
     if rank == 0:
         # ---- dominant kernel alone, CUDA events on its launching stream
