@@ -198,6 +198,12 @@ int tfhe_b200_keygen_ksk_words(tfhe_b200_ctx* ctx, const int32_t* out_key, const
 int tfhe_b200_keygen_ksk(tfhe_b200_ctx* ctx, const int32_t* out_key, const int32_t* in_key, double sigma, uint64_t seed,
                          int32_t* ksk_out);
 
+/* MKBootstrapKey (mk_internals.jl:442-461): RGSW.Expand (:304-345) of every party's uni-encryptions — the
+ * n*p*(p-1)*2*l^2 polynomial products, their sums, the transform and the load — on the device, no host round trip.
+ * uni_enc [p][6][n][l][N] in the order c0, c1, d0, d1, f0, f1 (mk_tgsw_encrypt, :185-227), public_b [p][l][N]
+ * (PublicKey.b, :115-139); bk_out (nullable) receives the coefficient form [p][n][l*(2p+2)][N]. */
+int tfhe_b200_mk_expand_load_bk(tfhe_b200_ctx* ctx, const int32_t* uni_enc, const int32_t* public_b, int32_t* bk_out);
+
 /* ---- one logical context over several GPUs ------------------------------------ */
 /* Gates are independent (gates.jl:15-18) and the evaluation keys are read-only, so a batch shards across GPUs with
  * no exchange step: keys are replicated at load, every call cuts its batch into contiguous shards of whole CTA

@@ -91,6 +91,24 @@ def test_levelised_adder32(keypair):
     assert sum(int(v) << i for i, v in enumerate(T.decrypt(sk, out["sum"].to_host()))) == (x + y) & 0xFFFFFFFF
 
 
+def test_cuda_graph_capture_of_a_circuit_replays_bit_identical(keypair):
+    """Circuit.compile captures every launch of the levelised evaluation in one CUDA graph; a
+    replay on new inputs must produce the ciphertexts of the eager evaluation, and the library must stay usable on other
+    streams afterwards."""
+    from tfhe_jl_b200.circuit import minimum_circuit
+    rng, sk, ck = keypair
+    cm = minimum_circuit(16)
+    compiled = cm.compile(ck)
+    for va, vb in ((2017, 42), (7, 40000)):
+        ia = {"a": T.encrypt(rng, sk, bits_of(va, 16)), "b": T.encrypt(rng, sk, bits_of(vb, 16))}
+        got = compiled.run(ia)["min"].to_host()
+        want = cm.run(ck, ia)["min"].to_host()
+        assert np.array_equal(got.data, want.data)
+        assert sum(int(v) << i for i, v in enumerate(T.decrypt(sk, got))) == min(va, vb)
+    x, y = T.encrypt(rng, sk, [True, False]), T.encrypt(rng, sk, [True, True])
+    assert np.array_equal(T.decrypt(sk, T.gate_nand(ck, x, y)), [False, True])
+
+
 def test_cloud_key_file_round_trip(keypair, tmp_path):
     """A saved cloud key reloaded into a fresh context evaluates to the same ciphertexts."""
     rng, sk, ck = keypair

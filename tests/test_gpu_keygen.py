@@ -157,3 +157,60 @@ def test_encrypt_on_device_feeds_the_gate_path_without_host_ciphertexts(keys80, 
     torch.cuda.synchronize()
     assert np.array_equal(ctx.decrypt(keys80.lwe_key, do.cpu().numpy()), ~(bits[0] & bits[1]))
     assert np.array_equal(dx.cpu().numpy(), ctx.encrypt(keys80.lwe_key, bits[0], P.lwe_sigma, 11))
+
+
+def uni_encryptions(rng, P, p):
+    """Uni-encryption-shaped random material for p parties (the expansion is exact integer arithmetic on whatever it is
+    given): uni_enc [p][6][n][l][N] in the order c0, c1, d0, d1, f0, f1, public_b [p][l][N]."""
+    return random_torus(rng, p, 6, P.n, P.l, N), random_torus(rng, p, P.l, N)
+
+
+def expand_reference(P, p, uni_enc, public_b):
+    """RGSW.Expand (mk_internals.jl:304-345) with the exact O(N^2) negacyclic product as ground truth."""
+    n, l = P.n, P.l
+    bk = np.zeros((p, n, l * (2 * p + 2), N), dtype=np.int32)
+    for i in range(p):
+        c0, c1, d0, d1, f0, f1 = uni_enc[i]
+        for j in range(n):
+            for jj in range(l):
+                for ii in range(p):
+                    xi, yi = jj * p + ii, l * p + jj * p + ii
+                    if ii == i:
+                        bk[i, j, xi], bk[i, j, yi] = d0[j, jj], d1[j, jj]
+                        continue
+                    u = O.decompose(wrap(public_b[ii, jj].astype(np.int64) - public_b[i, jj]), l, P.bgbit)   # :321
+                    x = d0[j, jj].astype(np.int64); y = np.zeros(N, dtype=np.int64)
+                    for r in range(l):
+                        x += O.polymul(u[r], f0[j, r], O.ROUTE_EXACT)                                        # :330
+                        y += O.polymul(u[r], f1[j, r], O.ROUTE_EXACT)                                        # :338
+                    bk[i, j, xi], bk[i, j, yi] = wrap(x), wrap(y)
+            bk[i, j, 2 * l * p:2 * l * p + l] = c0[j]
+            bk[i, j, 2 * l * p + l:] = c1[j]
+    return bk
+
+
+@pytest.mark.parametrize("p", [2, 4, 8])
+def test_mk_key_expansion_on_device_equals_exact_arithmetic(p):
+    P = O.small_params(O.MK_PARAMS[p], 2)
+    rng = np.random.default_rng(p)
+    uni_enc, public_b = uni_encryptions(rng, P, p)
+    ctx = T.Context(n=P.n, l=P.l, bgbit=P.bgbit, t=P.t, basebit=P.basebit, parties=p)
+    got = ctx.mk_expand_load_bk(uni_enc, public_b)
+    assert np.array_equal(got, expand_reference(P, p, uni_enc, public_b))
+
+
+def test_mk_cloud_key_device_expansion_equals_host_expansion_and_evaluates():
+    """examples/multikey.jl: the key expanded on the device is the key the round-1 host path builds, and it works."""
+    rng = np.random.default_rng(5)
+    params = T.mktfhe_parameters_2party
+    sks = [T.SecretKey(rng, params) for _ in range(2)]
+    shared = T.SharedKey(rng, params)
+    parts = [T.CloudKeyPart(rng, sk, shared) for sk in sks]
+    ck = T.MKCloudKey(parts)
+    ck_host = T.MKCloudKey(parts, host_expand=True)
+    assert np.array_equal(ck.bootstrap_key, ck_host.bootstrap_key)
+    m1 = rng.integers(0, 2, 12).astype(bool); m2 = rng.integers(0, 2, 12).astype(bool)
+    e1, e2 = T.mk_encrypt(rng, sks, m1), T.mk_encrypt(rng, sks, m2)
+    out = T.mk_gate_nand(ck, e1, e2)
+    assert np.array_equal(out.data, T.mk_gate_nand(ck_host, e1, e2).data)
+    assert np.array_equal(T.mk_decrypt(sks, out), ~(m1 & m2))

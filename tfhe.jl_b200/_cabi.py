@@ -92,6 +92,7 @@ def lib():
             "tfhe_b200_keygen_bk": (C.c_int, [vp, i32p, i32p, C.c_double, C.c_uint64, i32p]),
             "tfhe_b200_keygen_ksk_words": (C.c_int, [vp, i32p, i32p, i32p, i32p, i32p]),
             "tfhe_b200_keygen_ksk": (C.c_int, [vp, i32p, i32p, C.c_double, C.c_uint64, i32p]),
+            "tfhe_b200_mk_expand_load_bk": (C.c_int, [vp, i32p, i32p, i32p]),
             "tfhe_b200_multi_create": (C.c_int, [C.POINTER(CParams), C.POINTER(C.c_int), C.c_int, C.c_uint32, C.POINTER(vp)]),
             "tfhe_b200_multi_destroy": (None, [vp]),
             "tfhe_b200_multi_last_error": (C.c_char_p, [vp]),
@@ -324,6 +325,15 @@ class Context:
             self._ck(lib().tfhe_b200_keygen_bk_words(self._h, _addr(lwe_key), _addr(tlwe_key), _addr(a), _addr(noise), _addr(out)))
         else:
             self._ck(lib().tfhe_b200_keygen_bk(self._h, _addr(lwe_key), _addr(tlwe_key), float(sigma), int(seed), _addr(out)))
+        return out
+
+    def mk_expand_load_bk(self, uni_enc, public_b, keep=True):
+        """RGSW.Expand + transform + load of the MK bootstrapping key on the device (mk_internals.jl:304-345, 442-461).
+        uni_enc [p][6][n][l][N] (c0, c1, d0, d1, f0, f1), public_b [p][l][N]; returns [p][n][l*(2p+2)][N] when `keep`."""
+        p, n, l, N = self.parties, self.n, self.l, self.N
+        uni_enc = _host(uni_enc, (p, 6, n, l, N)); public_b = _host(public_b, (p, l, N))
+        out = np.empty((p, n, l * (2 * p + 2), N), dtype=np.int32) if keep else None
+        self._ck(lib().tfhe_b200_mk_expand_load_bk(self._h, _addr(uni_enc), _addr(public_b), _addr(out)))
         return out
 
     def keygen_ksk(self, out_key, in_key, sigma=None, seed=None, a=None, noise=None, keep=True):

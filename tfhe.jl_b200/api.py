@@ -358,12 +358,25 @@ def _decompose(x: np.ndarray, l: int, bgbit: int) -> np.ndarray:
 
 
 class MKCloudKey:                             # mk_api.jl:85-101
-    def __init__(self, ck_parts: Sequence[CloudKeyPart], device: Optional[int] = None, flags: int = _cabi.FLAG_SPLIT_FFT):
+    def __init__(self, ck_parts: Sequence[CloudKeyPart], device: Optional[int] = None, flags: int = _cabi.FLAG_SPLIT_FFT,
+                 host_expand: bool = False):
+        """The key expansion (RGSW.Expand, mk_internals.jl:304-345: n*p*(p-1)*2*l^2 polynomial products), the transform
+        and the load run on the device in one call (tfhe_b200_mk_expand_load_bk); ``host_expand=True`` keeps the
+        round-1 path (numpy loops around batched GPU products) for comparison."""
         params = ck_parts[0].params
         parties = len(ck_parts)
         assert parties <= params.max_parties                                              # mk_api.jl:94
         device = ck_parts[0].device if device is None else device
         self.parties, self.params = parties, params
+        if not host_expand:
+            names = ("c0", "c1", "d0", "d1", "f0", "f1")
+            uni_enc = np.stack([np.stack([part.uni_enc[k] for k in names]) for part in ck_parts])
+            public_b = np.stack([part.public_b for part in ck_parts])
+            self.keyswitch_key = np.stack([part.ks for part in ck_parts])
+            self.ctx = _context(params, parties, device, flags)
+            self.bootstrap_key = self.ctx.mk_expand_load_bk(uni_enc, public_b)
+            self.ctx.load_ksk(self.keyswitch_key)
+            return
         kctx = _mk_ctx(params, device)
         l, N, n, bgbit = params.bs_decomp_length, params.tlwe_polynomial_degree, params.lwe_size, params.bs_log2_base
         p = parties

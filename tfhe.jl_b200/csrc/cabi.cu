@@ -434,8 +434,13 @@ uint64_t tfhe_b200_kernel_launches(const tfhe_b200_ctx* ctx) { return ctx ? ctx-
 
 int tfhe_b200_synchronize(tfhe_b200_ctx* ctx) {
     if (!ctx) return TFHE_B200_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     CU(cudaDeviceSynchronize());
+    // nothing of this context is in flight any more: the next call need not wait for the previous user of the scratch
+    // buffers (this is also what makes a following CUDA-graph capture of *_dev calls legal: no event recorded outside
+    // the capture is waited on inside it)
+    ctx->scratch_busy = false;
     return 0;
 }
 

@@ -161,3 +161,73 @@ __global__ void ksk_messages_kernel(const int32_t* __restrict__ in_key, int32_t*
 }
 
 }  // namespace tfhe_b200
+
+// ---- MK key expansion on the device (RGSW.Expand, mk_internals.jl:304-345; MKBootstrapKey, :447-460) -----------------
+namespace tfhe_b200 {
+
+// u[jj][r] = digit r of (b_other[jj] - b_own[jj])   (mk_internals.jl:321, decompose tgsw.jl:99-117); one block per (jj, r)
+__global__ void mk_expand_digits_kernel(const int32_t* __restrict__ b_other, const int32_t* __restrict__ b_own,
+                                        int32_t* __restrict__ u, int l, int bgbit) {
+    const int jj = blockIdx.x / l, r = blockIdx.x % l;
+    uint32_t offset = 0;
+    for (int q = 1; q <= l; q++) offset += 1u << (32 - q * bgbit);
+    offset *= 1u << (bgbit - 1);
+    for (int x = threadIdx.x; x < kN; x += blockDim.x) {
+        const uint32_t v = (uint32_t)b_other[jj * kN + x] - (uint32_t)b_own[jj * kN + x] + offset;
+        u[(size_t)blockIdx.x * kN + x] = (int32_t)((v >> (32 - (r + 1) * bgbit)) & ((1u << bgbit) - 1)) - (1 << (bgbit - 1));
+    }
+}
+
+// out[j][jj] = base[j][jj] + sum_r u[jj][r] (*) f[j][r]      (mk_internals.jl:327-331 with base = d0, :338 with base = 0)
+// U: spectra of the digit polynomials, [l*l][512] (one piece: |u| <= Bg/2); F: spectra of f in two 16-bit pieces,
+// [n*l][2][512].  The sum over r is taken in the transform domain: l * (Bg/2) * 2^15 * N <= 2^33 keeps the rounding
+// error below 2^-10 (exactness), so lo + (hi << 16) is the exact integer sum of the l products.
+// One 64-thread block per (j, jj); the result goes straight into the expanded sample: poly index jj*p + other of the
+// x (which = 0) or y (which = 1) block of bk[own][j].
+__global__ void __launch_bounds__(64) mk_expand_mac_kernel(const double2* __restrict__ U, const double2* __restrict__ F,
+                                                           const int32_t* __restrict__ base, int32_t* __restrict__ bk_own,
+                                                           const double2* __restrict__ E, int l, int p, int other, int which) {
+    __shared__ double2 X1[512];
+    __shared__ double2 X2[kX2Elems];
+    const int t = threadIdx.x;
+    const int j = blockIdx.x / l, jj = blockIdx.x % l;
+    Twiddles w; w.load(E, t);
+    double2 lo[8], hi[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) { lo[e] = make_double2(0.0, 0.0); hi[e] = make_double2(0.0, 0.0); }
+    for (int r = 0; r < l; r++) {
+        const double2* u = U + ((size_t)jj * l + r) * kSpectrum + t;
+        const double2* f = F + ((size_t)j * l + r) * 2 * kSpectrum + t;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const double2 uv = __ldg(u + e * 64);
+            cmac(lo[e], uv, __ldg(f + e * 64));
+            cmac(hi[e], uv, __ldg(f + kSpectrum + e * 64));
+        }
+    }
+    fft512_inverse(lo, w, X1, X2, t, 0);
+    fft512_inverse(hi, w, X1, X2, t, 0);
+    const size_t spolys = (size_t)l * (2 * p + 2);
+    int32_t* o = bk_own + ((size_t)j * spolys + (size_t)which * l * p + (size_t)jj * p + other) * kN;
+    const int32_t* b = base ? base + ((size_t)j * l + jj) * kN : nullptr;
+#pragma unroll
+    for (int m = 0; m < 8; m++) {
+        const int x = t + 64 * m;
+        const uint32_t vl = round_to_u32_fast<true>(lo[m].x) + (round_to_u32_fast<true>(hi[m].x) << 16);
+        const uint32_t vh = round_to_u32_fast<true>(-lo[m].y) + (round_to_u32_fast<true>(-hi[m].y) << 16);
+        o[x] = (int32_t)(vl + (b ? (uint32_t)b[x] : 0u));
+        o[x + 512] = (int32_t)(vh + (b ? (uint32_t)b[x + 512] : 0u));
+    }
+}
+
+// the parts of an expanded sample that are plain copies: x[jj][own] = d0[jj], y[jj][own] = d1[jj] (:327, :336),
+// c0, c1 (:341-342).  src [n][l][N]; dst poly index = first + jj*step inside sample j of bk[own].
+__global__ void mk_expand_copy_kernel(const int32_t* __restrict__ src, int32_t* __restrict__ bk_own, int l, int p, int first, int step) {
+    const int j = blockIdx.x / l, jj = blockIdx.x % l;
+    const size_t spolys = (size_t)l * (2 * p + 2);
+    const int32_t* s = src + ((size_t)j * l + jj) * kN;
+    int32_t* o = bk_own + ((size_t)j * spolys + first + (size_t)jj * step) * kN;
+    for (int x = threadIdx.x; x < kN; x += blockDim.x) o[x] = s[x];
+}
+
+}  // namespace tfhe_b200

@@ -90,6 +90,15 @@ def main():
     assert value_of(T.decrypt(sk, out.to_host())) == (x + y) & 0xFFFFFFFF
     res["adder32_levelised_ms"], res["adder32_levels"] = ms, ca.depth
 
+    # ... and captured as one CUDA graph each (Circuit.compile)
+    gm, ga = cm.compile(ck), ca.compile(ck)
+    out, ms = timed(lambda: gm.run(ia)["min"])
+    assert value_of(T.decrypt(sk, out.to_host())) == 42
+    res["tutorial_min16_graph_ms"] = ms
+    out, ms = timed(lambda: ga.run(ib)["sum"])
+    assert value_of(T.decrypt(sk, out.to_host())) == (x + y) & 0xFFFFFFFF
+    res["adder32_graph_ms"] = ms
+
     if os.environ.get("CPU", "1") == "1":
         from oracle import oracle as O
         keys = O.keygen(O.PARAMS_80, 5)
