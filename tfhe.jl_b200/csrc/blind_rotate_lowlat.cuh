@@ -46,7 +46,9 @@ __global__ void __launch_bounds__(64 * 2 * L, 1) blind_rotate_lowlat_kernel(Blin
     double2* X1 = xbuf + (size_t)grp * (kSpectrum + kX2Elems);
     double2* X2 = X1 + kSpectrum;
     const unsigned long long g = blockIdx.x;
-    Twiddles w; w.load(A.E, t);
+    // four groups (256 threads) leave 255 registers per thread: room for the full twiddle set (no twiddle is re-derived
+    // inside the two transforms of the critical path); six groups (l = 3, 384 threads, 168 registers) keep the compact set
+    typename std::conditional<L == 2, TwiddlesFull, Twiddles>::type w; w.load(A.E, t);
 
     // output group o = (c2, pc) reads, for q = (c, r), the spectrum BK[i][r][c][c2][pc]
     const int c2 = grp / NP, pc = grp % NP;
