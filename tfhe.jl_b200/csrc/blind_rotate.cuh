@@ -374,169 +374,6 @@ __device__ __forceinline__ void extern_product_step_os(int32_t* acc, int abar, B
     if (PROBE) pr[3] += clock64() - c0;
 }
 
-// ---- K2 for PAIRS of gates: every key spectrum read from shared memory feeds two gates --------------------------------
-//
-// After the producer warpgroup the step above is bound by the shared-memory pipe (79 % of peak, ncu), and 30 % of its
-// wavefronts are key reads: four groups each read all 16 key spectra of an iteration.  Tensor memory is addressed by
-// lane, and warps w and w+4 — thread t of group g and thread t of group g+2 — own the SAME lanes.  So the forward
-// spectra of gate g+2, parked in TMEM by their owner, can be read by group g at no shared-memory cost (tcgen05.ld runs
-// at 234 B/clk beside the LDS pipe, tools/tmem_cp_test.cu).  The pair (g, g+2) therefore splits the second phase by
-// OUTPUT COMPONENT instead of by gate:
-//
-//   phase 1   every group: the 2L forward transforms of its own gate -> its TMEM slot               | pair barrier
-//   phase 2   group g   : component c' = 0 of BOTH gates;   group g+2: component c' = 1 of BOTH gates
-//             for piece = lo, hi:  (S, P) = sum_q (F_q[self], F_q[peer]) * BK[r][c][c'][piece]   one 8 KB spectrum per q,
-//                                  loaded ONCE into registers, used for both gates
-//                                  inverse transform S, P; lo: rounded words parked in TMEM; hi: acc[.][c'] += lo + (hi << 16)
-//                                                                                               | pair barrier
-//
-// Key reads drop from 16 to 8 spectra per thread and iteration (3 392 -> 2 880 shared-memory wavefronts per gate and
-// iteration), each group still runs 2L forward and 4 inverse transforms, and the groups of a pair meet twice per
-// iteration.  The ring holds single spectra in the order (piece, q, c'); a spectrum is consumed by the two groups of one
-// role only (4 warps), which alternate over the stages: role c' uses the stages of parity c' (STAGES is even).
-template <int L, int STAGES> struct BkSpectrumRing {
-    static_assert(STAGES % 2 == 0, "the two roles alternate over the stages");
-    static constexpr int Q = 2 * L, kUnitsPerIter = 4 * Q;
-    const double2* ring; uint64_t* full; uint64_t* empty;
-    const double2* bk;        // start of the key: [n_iter][L][2][2][2][512]
-    int total;                // spectra in the whole walk
-    int stage; uint32_t phase;   // consumer cursor: the next spectrum of this group's role
-    uint32_t ready_next = 0;
-    int iss = 0, iss_stage = 0, iss_round = 0, iss_i = 0, iss_u = 0;   // producer cursor
-
-    __device__ __forceinline__ void produce_all() {
-        while (iss < total) {
-            // unit u of an iteration = (piece, q = (c, r), c'); stored as spectrum ((r*2 + c)*2 + c')*2 + piece
-            const int c2 = iss_u & 1, q = (iss_u >> 1) % Q, piece = (iss_u >> 1) / Q;
-            const int r = q % L, c = q / L;
-            const size_t off = ((size_t)iss_i * kUnitsPerIter + (size_t)(((r * 2 + c) * 2 + c2) * 2 + piece)) * kSpectrum;
-            if (iss_round >= 1) mbar_wait(empty + iss_stage, (uint32_t)(iss_round - 1) & 1u);
-            mbar_arrive_expect_tx(full + iss_stage, kSpectrum * 16);
-            bulk_copy_g2s(const_cast<double2*>(ring) + (size_t)iss_stage * kSpectrum, bk + off, kSpectrum * 16, full + iss_stage);
-            iss++;
-            if (++iss_stage == STAGES) { iss_stage = 0; iss_round++; }
-            if (++iss_u == kUnitsPerIter) { iss_u = 0; iss_i++; }
-        }
-    }
-    __device__ __forceinline__ const double2* acquire() {
-        if (!ready_next) mbar_wait_poll(full + stage, phase);
-        const int ns = stage + 2 >= STAGES ? stage + 2 - STAGES : stage + 2;
-        uint32_t done;
-        asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(smem_u32(full + ns)), "r"(stage + 2 >= STAGES ? phase ^ 1u : phase) : "memory");
-        ready_next = done;   // the answer is back long before the next acquire needs it
-        return ring + (size_t)stage * kSpectrum;
-    }
-    __device__ __forceinline__ void release() {
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(empty + stage);
-        stage += 2;
-        if (stage >= STAGES) { stage -= STAGES; phase ^= 1; }
-    }
-};
-
-__device__ __forceinline__ void tmem_st_words16(uint32_t taddr, const uint32_t (&v)[16]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
-                   "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_words16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                 : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void pair_sync(int pair_bar) { asm volatile("bar.sync %0, 128;" ::"r"(pair_bar) : "memory"); }
-
-// acc_self / acc_peer: the accumulators of this group's gate and of its partner's; tm_self / tm_peer: the TMEM slots of
-// their forward spectra; tm_scr: 32 private TMEM columns; role = the output component this group computes.
-template <int L, int BGBIT, class RING, class W>
-__device__ __forceinline__ void extern_product_step_pair(int32_t* acc_self, int32_t* acc_peer, int abar, RING& ring, const W& w,
-                                                         double2* X1, double2* X2, uint32_t tm_self, uint32_t tm_peer,
-                                                         uint32_t tm_scr, int role, int t, int bar_id, int pair_bar) {
-    constexpr int Q = 2 * L;
-    constexpr uint32_t offset = decomp_offset<L, BGBIT>();
-    const int s = abar & 2047;
-    // ---- phase 1: the Q forward transforms of this group's own gate ----
-#pragma unroll 1
-    for (int c = 0; c < 2; c++) {
-        const int32_t* p = acc_self + c * kN;
-        uint32_t tl[8], th[8];
-#pragma unroll
-        for (int m = 0; m < 8; m++) {
-            int j = t + 64 * m;
-            tl[m] = (uint32_t)rot_coeff(p, j, s) - (uint32_t)p[j] + offset;                 // bootstrap.jl:21
-            th[m] = (uint32_t)rot_coeff(p, j + 512, s) - (uint32_t)p[j + 512] + offset;
-        }
-#pragma unroll 1
-        for (int r = 0; r < L; r++) {
-            double2 a[8];
-#pragma unroll
-            for (int m = 0; m < 8; m++)
-                a[m] = make_double2(digit_f64<BGBIT>(tl[m], r), -digit_f64<BGBIT>(th[m], r));   // tgsw.jl:104-116
-            const int q = c * L + r;
-            fft512_forward_t<1>(a, w, X1 + (q & 1) * kSpectrum, X2, t, bar_id, NoPrefetch());
-            tmem_store_spectrum(tm_self + (uint32_t)(q * 32), a);
-        }
-    }
-    tmem_wait_st();
-    tmem_fence_before_sync();
-    pair_sync(pair_bar);   // both gates' spectra are in TMEM; every read of both accumulators for this iteration is done
-    tmem_fence_after_sync();
-    // ---- phase 2: output component `role` of both gates, one 16-bit piece at a time ----
-    int32_t* ps = acc_self + role * kN;
-    int32_t* pp = acc_peer + role * kN;
-#pragma unroll 1
-    for (int piece = 0; piece < 2; piece++) {
-        double2 aS[8], aP[8];
-#pragma unroll
-        for (int e = 0; e < 8; e++) { aS[e] = make_double2(0.0, 0.0); aP[e] = make_double2(0.0, 0.0); }
-#pragma unroll
-        for (int q = 0; q < Q; q++) {
-            const double2* b = ring.acquire() + t;
-            double2 kv[8], F[8];
-#pragma unroll
-            for (int e = 0; e < 8; e++) kv[e] = b[e * 64];
-            tmem_load_spectrum(tm_self + (uint32_t)(q * 32), F);
-#pragma unroll
-            for (int e = 0; e < 8; e++) cmac(aS[e], F[e], kv[e]);                           // tgsw.jl:128
-            tmem_load_spectrum(tm_peer + (uint32_t)(q * 32), F);
-#pragma unroll
-            for (int e = 0; e < 8; e++) cmac(aP[e], F[e], kv[e]);
-            ring.release();
-        }
-        fft512_inverse_t<1>(aS, w, X1, X2, t, bar_id);
-        fft512_inverse_t<1>(aP, w, X1 + kSpectrum, X2, t, bar_id);
-        uint32_t vS[16], vP[16];
-#pragma unroll
-        for (int m = 0; m < 8; m++) {                                                       // polynomials.jl:115-116
-            vS[m] = round_to_u32_fast<true>(aS[m].x); vS[8 + m] = round_to_u32_fast<true>(-aS[m].y);
-            vP[m] = round_to_u32_fast<true>(aP[m].x); vP[8 + m] = round_to_u32_fast<true>(-aP[m].y);
-        }
-        if (piece == 0) {
-            tmem_st_words16(tm_scr, vS);
-            tmem_st_words16(tm_scr + 16, vP);
-            tmem_wait_st();
-        } else {
-            uint32_t lS[16], lP[16];
-            tmem_ld_words16(tm_scr, lS);
-            tmem_ld_words16(tm_scr + 16, lP);
-            tmem_wait_ld();
-#pragma unroll
-            for (int m = 0; m < 8; m++) {                                                   // bootstrap.jl:22
-                const int j = t + 64 * m;
-                ps[j] = (int32_t)((uint32_t)ps[j] + lS[m] + (vS[m] << 16));
-                ps[j + 512] = (int32_t)((uint32_t)ps[j + 512] + lS[8 + m] + (vS[8 + m] << 16));
-                pp[j] = (int32_t)((uint32_t)pp[j] + lP[m] + (vP[m] << 16));
-                pp[j + 512] = (int32_t)((uint32_t)pp[j + 512] + lP[8 + m] + (vP[8 + m] << 16));
-            }
-        }
-    }
-    tmem_fence_before_sync();
-    pair_sync(pair_bar);   // both accumulators are complete and the TMEM slots are free before the next rotation
-    tmem_fence_after_sync();
-}
-
 // ---- K4T: key switch of a TILE of 64 ciphertexts per CTA (keyswitch.jl:45-80) ---------------------------------
 // keyswitch_kernel (one CTA per ciphertext) gathers 12.3 MB of table rows per ciphertext from L2 and runs at the
 // L2 bandwidth limit (13.9 TB/s).  Here a CTA owns 64 ciphertexts and streams the WHOLE table once through shared
@@ -658,21 +495,17 @@ struct BlindRotateArgs {
 __host__ __device__ constexpr int group_smem_bytes(int /*NP*/) { return (kSpectrum + kX2Elems) * 16 + 2 * kN * 4; }
 // TM == 3 (output-stationary step): two X1 buffers per group, used alternately (SYNC == 1 transforms)
 __host__ __device__ constexpr size_t br_group_bytes(int NP, int TM) {
-    return (size_t)group_smem_bytes(NP) + (TM >= 3 ? kSpectrum * 16 : 0);
-}
-// TM == 4 (pairs of gates): the ring holds single spectra (8 KB stages) and needs 2 * STAGES barriers
-__host__ __device__ constexpr size_t br_ring_bytes(int STAGES, int TM) {
-    return TM == 4 ? (size_t)STAGES * kSpectrum * 16 + 256 : (size_t)STAGES * kChunkBytes + 128;
+    return (size_t)group_smem_bytes(NP) + (TM == 3 ? kSpectrum * 16 : 0);
 }
 __host__ __device__ constexpr size_t br_smem_bytes(int NP, int G, int STAGES, int n_pad, int TM = 0) {
-    return br_ring_bytes(STAGES, TM) + (size_t)G * (br_group_bytes(NP, TM) + n_pad * 4);
+    return (size_t)STAGES * kChunkBytes + 128 + (size_t)G * (br_group_bytes(NP, TM) + n_pad * 4);
 }
 
 // TMEM columns to allocate when the accumulators live in tensor memory: warps that share a lane quarter
 // (warp % 4) get disjoint column ranges of 64*NP columns each; allocations are powers of two.
-__host__ __device__ constexpr int br_tmem_cols_per_warp(int NP, int L, int TM) { return TM >= 3 ? 2 * L * 32 : 64 * NP; }
+__host__ __device__ constexpr int br_tmem_cols_per_warp(int NP, int L, int TM) { return TM == 3 ? 2 * L * 32 : 64 * NP; }
 __host__ __device__ constexpr int br_tmem_cols(int NP, int G, int L = 2, int TM = 1) {
-    int need = ((2 * G + 3) / 4) * (br_tmem_cols_per_warp(NP, L, TM) + (TM == 4 ? 32 : 0)), c = 32;   // TM == 4: + scratch
+    int need = ((2 * G + 3) / 4) * br_tmem_cols_per_warp(NP, L, TM), c = 32;
     while (c < need) c *= 2;
     return c;
 }
@@ -690,10 +523,8 @@ __global__ void __launch_bounds__(64 * G + ((OPT >> 7) & 1) * 128, 1) blind_rota
     __shared__ uint32_t s_tmem_base;
     // TM: 0 = accumulators in registers, 1 = all in TMEM, 2 = component 1 in TMEM,
     //     3 = output-stationary step (extern_product_step_os; NP == 2): forward spectra in TMEM, full twiddle set
-    //     4 = the same for PAIRS of gates (extern_product_step_pair): every key spectrum read feeds two gates
     constexpr bool kUseTmem = TM != 0;
-    static_assert(TM < 3 || NP == 2, "the output-stationary steps are the two-piece path");
-    static_assert(TM != 4 || (G == 4 && PWARP && MODE == 0), "pairs of gates: 4 gates per CTA, producer warpgroup");
+    static_assert(TM != 3 || NP == 2, "the output-stationary step is the two-piece path");
     constexpr int kTmemCols = br_tmem_cols(NP, G, L, TM);
     static_assert(kTmemCols <= 512, "tensor memory: too many gates per CTA");
     constexpr size_t kGroupBytes = br_group_bytes(NP, TM);
@@ -701,15 +532,13 @@ __global__ void __launch_bounds__(64 * G + ((OPT >> 7) & 1) * 128, 1) blind_rota
         if ((threadIdx.x >> 5) == 0) tmem_alloc<kTmemCols>(&s_tmem_base);
         tmem_fence_before_sync();
     }
-    constexpr size_t kStageBytes = TM == 4 ? kSpectrum * 16 : kChunkBytes;
     double2* ring = reinterpret_cast<double2*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * kStageBytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)STAGES * kChunkBytes);
     uint64_t* empty = full + STAGES;
-    unsigned char* groups = smem_raw + br_ring_bytes(STAGES, TM);
+    unsigned char* groups = smem_raw + (size_t)STAGES * kChunkBytes + 128;
 
     if (threadIdx.x == 0) {
-        // a stage is released by every compute warp — in pair mode by the 4 warps of the two groups that share its role
-        for (int s = 0; s < STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, TM == 4 ? G : 2 * G); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 2 * G); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -720,13 +549,11 @@ __global__ void __launch_bounds__(64 * G + ((OPT >> 7) & 1) * 128, 1) blind_rota
         tm = s_tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * br_tmem_cols_per_warp(NP, L, TM));
     }
     BkFromRing<L, NP, STAGES, TM == 3 ? 1 : 0, PROBE, PWARP> bk{ring, full, empty, A.bk_fft, A.n_iter * 2 * L * NP, 0, 0u, threadIdx.x == 0};
-    // pair mode: role = the output component this group computes (groups 0, 1: c' = 0; groups 2, 3: c' = 1)
-    BkSpectrumRing<L, TM == 4 ? STAGES : 2> sring{ring, full, empty, A.bk_fft, A.n_iter * 8 * L, (int)(threadIdx.x >> 7) & 1, 0u};
     if (PWARP) {
         static_assert(!PWARP || G == 4, "register rebalancing assumes two full compute warpgroups");
         if ((threadIdx.x >> 5) >= 2 * G) {
             asm volatile("setmaxnreg.dec.sync.aligned.u32 24;" ::: "memory");
-            if (threadIdx.x == 64 * G) { if constexpr (TM == 4) sring.produce_all(); else bk.produce_all(); }
+            if (threadIdx.x == 64 * G) bk.produce_all();
             return;   // the compute warps meet at named barriers only from here on
         }
         asm volatile("setmaxnreg.inc.sync.aligned.u32 240;" ::: "memory");
@@ -737,13 +564,13 @@ __global__ void __launch_bounds__(64 * G + ((OPT >> 7) & 1) * 128, 1) blind_rota
     const int t = threadIdx.x & 63, grp = threadIdx.x >> 6;
     const int bar_id = grp + 1;
     unsigned char* base = groups + (size_t)grp * (kGroupBytes + A.n_pad * 4);
-    double2* X1 = reinterpret_cast<double2*>(base);                      // TM >= 3: two buffers, used alternately
-    double2* X2 = X1 + (TM >= 3 ? 2 : 1) * kSpectrum;
+    double2* X1 = reinterpret_cast<double2*>(base);                      // TM == 3: two buffers, used alternately
+    double2* X2 = X1 + (TM == 3 ? 2 : 1) * kSpectrum;
     int32_t* acc = reinterpret_cast<int32_t*>(X2 + kX2Elems);
     int32_t* bara = acc + 2 * kN;
     const unsigned long long g = (unsigned long long)blockIdx.x * G + grp;
     const bool valid = g < A.count;   // a group without a gate still walks the ring (on zeros) to keep the lockstep
-    typename std::conditional<TM >= 3, TwiddlesFull, Twiddles>::type w; w.load(A.E, t);
+    typename std::conditional<TM == 3, TwiddlesFull, Twiddles>::type w; w.load(A.E, t);
 
     if (!valid) {
         for (int x = t; x < 2 * kN; x += 64) acc[x] = 0;
@@ -783,13 +610,7 @@ __global__ void __launch_bounds__(64 * G + ((OPT >> 7) & 1) * 128, 1) blind_rota
     if (PROBE) t_start = clock64();
 #pragma unroll 1
     for (int i = 0; i < A.n_iter; i++) {   // bootstrap.jl:19-23
-        if constexpr (TM == 4) {
-            // partner = group grp ^ 2 (same TMEM lanes); its accumulator sits 2 group strides away in shared memory
-            const long long pstride = (long long)(kGroupBytes + A.n_pad * 4) / 4 * ((grp & 2) ? -2 : 2);
-            const uint32_t qcols = 2 * L * 32, slot = (threadIdx.x >> 7) & 1, lane_base = tm - slot * qcols;
-            extern_product_step_pair<L, BGBIT>(acc, acc + pstride, bara[i], sring, w, X1, X2, tm, lane_base + (1 - slot) * qcols,
-                                               lane_base + 2 * qcols + slot * 32, (int)slot, t, bar_id, 5 + (grp & 1));
-        } else if constexpr (TM == 3) extern_product_step_os<L, BGBIT, 1, PROBE>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id, pr);
+        if constexpr (TM == 3) extern_product_step_os<L, BGBIT, 1, PROBE>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id, pr);
         else if constexpr (TM != 0) extern_product_step_tmem<L, BGBIT, NP, (TM == 2 && NP == 2) ? 1 : 0>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id);
         else extern_product_step<L, BGBIT, NP, true, true>(acc, bara[i], bk, w, X1, X2, t, bar_id);
     }

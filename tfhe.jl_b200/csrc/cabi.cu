@@ -139,7 +139,6 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
             case 304:
                 if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3>(ctx, A, s);
                 else return launch_br_g<L, BGBIT, NP, 4, 6, MODE>(ctx, A, s);
-            case 504: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 10, MODE, 4, 128>(ctx, A, s); else break;   // pairs of gates share the key reads
             case 1304:                                                                  // clock64 phase probe of the default kernel
                 if constexpr (NP == 2 && L == 2 && MODE == 0) {
                     BlindRotateArgs B = A;
