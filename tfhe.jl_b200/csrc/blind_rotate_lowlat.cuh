@@ -21,9 +21,16 @@
 
 namespace tfhe_b200 {
 
+// Key slots per output group.  All 2l key spectra of an output are prefetched during the previous iteration when that
+// fits (80-bit set, either mode; 128-bit set with one piece).  The 128-bit set with two pieces would need 4 x 6 x 8 KB
+// = 192 KB of key slots beside 102 KB of exchange buffers: there every output group walks its 6 spectra through a ring
+// of 3 slots, refilling a slot as soon as the whole group has consumed it (one extra 64-thread barrier per refill).
+template <int L, int NP> __host__ __device__ constexpr int br_lowlat_key_slots() {
+    return ((2 * NP) * (2 * L) * 8 + (2 * L) * 17 + 12 <= 227) ? 2 * L : 3;
+}
 template <int L, int NP> __host__ __device__ constexpr size_t br_lowlat_smem_bytes(int n_pad) {
-    return (size_t)(2 * NP) * (2 * L) * kSpectrum * 16   // key slots [output][digit polynomial]
-           + 128                                         // mbarriers
+    return (size_t)(2 * NP) * br_lowlat_key_slots<L, NP>() * kSpectrum * 16   // key slots [output][slot]
+           + 256                                         // mbarriers [output][slot]
            + (size_t)(2 * L) * (kSpectrum + kX2Elems) * 16   // X1, X2 per group
            + 2 * kN * 4 + (size_t)n_pad * 4;             // accumulator, modulus-switched mask
 }
@@ -35,9 +42,11 @@ __global__ void __launch_bounds__(64 * 2 * L, 1) blind_rotate_lowlat_kernel(Blin
     static_assert(NO <= NG, "needs at least as many groups as output spectra");
     constexpr uint32_t offset = decomp_offset<L, BGBIT>();
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int KS = br_lowlat_key_slots<L, NP>();   // key slots per output group (== NG: everything prefetched)
+    static_assert(NO * KS * 8 <= 256, "mbarrier area");
     double2* keys = reinterpret_cast<double2*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NO * NG * kSpectrum * 16);
-    double2* xbuf = reinterpret_cast<double2*>(smem_raw + (size_t)NO * NG * kSpectrum * 16 + 128);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NO * KS * kSpectrum * 16);   // [output][slot]
+    double2* xbuf = reinterpret_cast<double2*>(smem_raw + (size_t)NO * KS * kSpectrum * 16 + 256);
     int32_t* acc = reinterpret_cast<int32_t*>(xbuf + (size_t)NG * (kSpectrum + kX2Elems));
     int32_t* bara = acc + 2 * kN;
 
@@ -52,19 +61,21 @@ __global__ void __launch_bounds__(64 * 2 * L, 1) blind_rotate_lowlat_kernel(Blin
 
     // output group o = (c2, pc) reads, for q = (c, r), the spectrum BK[i][r][c][c2][pc]
     const int c2 = grp / NP, pc = grp % NP;
-    auto issue_keys = [&](int i) {
-        mbar_arrive_expect_tx(full + grp, (uint32_t)(NG * kSpectrum * 16));
-#pragma unroll
-        for (int q = 0; q < NG; q++) {
-            const int c = q / L, r = q % L;
-            const double2* src = A.bk_fft + ((((size_t)i * L + r) * 2 + c) * 2 * NP + (size_t)c2 * NP + pc) * kSpectrum;
-            bulk_copy_g2s(keys + ((size_t)grp * NG + q) * kSpectrum, src, kSpectrum * 16, full + grp);
-        }
+    // spectrum number seq = i*NG + q of this output group goes to slot seq % KS; its barrier completes for the
+    // (seq / KS)-th time when the copy lands
+    const int total = A.n_iter * NG;
+    auto issue_key = [&](int seq) {
+        const int i = seq / NG, q = seq % NG, slot = seq % KS;
+        const int c = q / L, r = q % L;
+        const double2* src = A.bk_fft + ((((size_t)i * L + r) * 2 + c) * 2 * NP + (size_t)c2 * NP + pc) * kSpectrum;
+        mbar_arrive_expect_tx(full + grp * KS + slot, (uint32_t)(kSpectrum * 16));
+        bulk_copy_g2s(keys + ((size_t)grp * KS + slot) * kSpectrum, src, kSpectrum * 16, full + grp * KS + slot);
     };
-    if (threadIdx.x < NO) mbar_init(full + threadIdx.x, 1);
+    if (threadIdx.x < NO * KS) mbar_init(full + threadIdx.x, 1);
     if (threadIdx.x == 0) mbar_fence_init();
     __syncthreads();
-    if (grp < NO && t == 0 && A.n_iter > 0) issue_keys(0);
+    if (grp < NO && t == 0)
+        for (int seq = 0; seq < KS && seq < total; seq++) issue_key(seq);
 
     // gate prologue (gates.jl) + modulus switch (bootstrap.jl:74-75), all threads of the CTA
     {
@@ -112,20 +123,26 @@ __global__ void __launch_bounds__(64 * 2 * L, 1) blind_rotate_lowlat_kernel(Blin
         __syncthreads();   // A: all spectra published, all reads of acc done
         double2 o[8];
         if (grp < NO) {
-            mbar_wait(full + grp, (uint32_t)i & 1u);
 #pragma unroll
             for (int e = 0; e < 8; e++) o[e] = make_double2(0.0, 0.0);
 #pragma unroll
             for (int q = 0; q < NG; q++) {   // same summation order as K3: c outer, r inner
+                const int seq = i * NG + q, slot = KS == NG ? q : seq % KS;
+                mbar_wait(full + grp * KS + slot, (uint32_t)(KS == NG ? i : seq / KS) & 1u);
                 const double2* F = xbuf + (size_t)q * (kSpectrum + kX2Elems) + t;
-                const double2* K = keys + ((size_t)grp * NG + q) * kSpectrum + t;
+                const double2* K = keys + ((size_t)grp * KS + slot) * kSpectrum + t;
 #pragma unroll
                 for (int e = 0; e < 8; e++) cmac(o[e], F[e * 64], K[e * 64]);                            // tgsw.jl:128
+                if (KS < NG) {   // ring of slots: refill this one as soon as the whole group has consumed it
+                    group_sync(bar_id);
+                    if (t == 0 && seq + KS < total) issue_key(seq + KS);
+                }
             }
         }
         __syncthreads();   // B: spectra and key slots consumed
         if (grp < NO) {
-            if (t == 0 && i + 1 < A.n_iter) issue_keys(i + 1);   // lands during the inverse + next forward transform
+            if (KS == NG && t == 0 && i + 1 < A.n_iter)   // lands during the inverse + next forward transform
+                for (int q = 0; q < NG; q++) issue_key((i + 1) * NG + q);
             fft512_inverse(o, w, X1, X2, t, bar_id);
             int32_t* pa = acc + c2 * kN;
 #pragma unroll
