@@ -19,7 +19,7 @@ if [ "${EXTRA:-1}" = "1" ]; then
   timeout 900 python tools/sweep.py > gpurun_out/sweep.json 2> gpurun_out/sweep.err
 fi
 NCU="ncu --set full --import-source on --clock-control none -f"
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras --batch 65536"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras"   # the default workload (2^17 gates per launch)
 $CMD > gpurun_out/plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 $CMD > gpurun_out/plain2.log 2>&1 && $NCU -k regex:blind_rotate_kernel -s 1 -c 1 -o gpurun_out/prof_blind_rotate $CMD > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log 2>/dev/null; cat gpurun_out/smoke.log 2>/dev/null
