@@ -1,7 +1,7 @@
 # crosscheck.jl — pins libtfhe_b200.so against the REAL TFHE.jl (SURVEY.md §8c: ciphertext-level parity with
 # TFHE.jl itself cannot be pinned in the build image because Julia is not installed there).
 #
-#     julia --project=/path/to/TFHE.jl tfhe.jl_b200/julia/crosscheck.jl [count]
+#     julia --project=/path/to/TFHE.jl tfhe.jl_b200/julia/crosscheck.jl [count [fixture_dir]]
 #
 # Generates keys and ciphertexts with TFHE.jl (MersenneTwister(123), as test/runtests.jl:27), exports the keys in
 # the C ABI's int32 layouts, runs every bootstrapped gate both through TFHE.jl and through the library on the
@@ -52,4 +52,22 @@ end
 want = tomat([TFHE.gate_mux(ck, x[g], y[g], z[g]) for g in 1:count])
 got = B.c_gate(ctx, B.MUX, tomat(x), tomat(y), tomat(z), count)
 println("MUX    ", want == got ? "identical" : "MISMATCH"); ok &= want == got
+
+# Optional second argument: a directory to receive reference-pinned fixtures (raw little-endian Int32 files + a manifest)
+# for tests/test_reference_fixtures.py — commit them as tests/golden/tfhejl/ and the oracle is pinned to TFHE.jl itself.
+if length(ARGS) > 1
+    dir = ARGS[2]; mkpath(dir)
+    dump(name, a) = open(io -> write(io, Array{Int32}(a)), joinpath(dir, name * ".bin"), "w")
+    dump("lwe_key", sk.key.key); dump("bk", bk); dump("ksk", ks)
+    dump("x", tomat(x)); dump("y", tomat(y)); dump("z", tomat(z))
+    for (op, ref) in binary
+        dump("out_" * string(op), tomat([ref(ck, x[g], y[g]) for g in 1:count]))
+    end
+    dump("out_MUX", want)
+    open(joinpath(dir, "manifest.json"), "w") do io
+        print(io, "{\"source\": \"TFHE.jl via crosscheck.jl, MersenneTwister(123)\", \"count\": $count, \"n\": $n, \"N\": $N, \"k\": $k, \"l\": $l, ",
+              "\"bgbit\": $(p.bs_log2_base), \"t\": $t, \"basebit\": $(p.ks_log2_base), \"gates\": [",
+              join(["\"" * string(op) * "\"" for (op, _) in binary], ", "), ", \"MUX\"]}")
+    end
+end
 exit(ok ? 0 : 1)
