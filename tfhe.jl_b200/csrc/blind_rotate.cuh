@@ -301,6 +301,62 @@ __device__ __forceinline__ void tmem_ld_spectrum_finish(int (&r0)[16], int (&r1)
     }
 }
 
+// The same iteration with the transforms taken in pairs (fft512_forward_dual / _inverse_dual): the two digit polynomials
+// of an accumulator component (l = 2), and the two pieces of an output component.
+template <int BGBIT, class BK, class W>
+__device__ __forceinline__ void extern_product_step_os_dual(int32_t* acc, int abar, BK& bk, const W& w, double2* X1, double2* X2,
+                                                            uint32_t tm, int t, int bar_id) {
+    constexpr int L = 2, Q = 4;
+    constexpr uint32_t offset = decomp_offset<L, BGBIT>();
+    const int s = abar & 2047;
+#pragma unroll 1
+    for (int c = 0; c < 2; c++) {
+        const int32_t* p = acc + c * kN;
+        double2 a[8], b[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            const int j = t + 64 * m;
+            const uint32_t tl = (uint32_t)rot_coeff(p, j, s) - (uint32_t)p[j] + offset;                 // bootstrap.jl:21
+            const uint32_t th = (uint32_t)rot_coeff(p, j + 512, s) - (uint32_t)p[j + 512] + offset;
+            a[m] = make_double2(digit_f64<BGBIT>(tl, 0), -digit_f64<BGBIT>(th, 0));                     // tgsw.jl:104-116
+            b[m] = make_double2(digit_f64<BGBIT>(tl, 1), -digit_f64<BGBIT>(th, 1));
+        }
+        fft512_forward_dual(a, b, w, X1, X1 + kSpectrum, X2, t, bar_id);
+        tmem_store_spectrum(tm + (uint32_t)((c * L) * 32), a);
+        tmem_store_spectrum(tm + (uint32_t)((c * L + 1) * 32), b);
+    }
+    tmem_wait_st();
+#pragma unroll 1
+    for (int c2 = 0; c2 < 2; c2++) {
+        double2 lo[8], hi[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) { lo[e] = make_double2(0.0, 0.0); hi[e] = make_double2(0.0, 0.0); }
+        int r0[16], r1[16];
+        tmem_ld_spectrum_raw(tm, r0, r1);
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            double2 F[8];
+            tmem_ld_spectrum_finish(r0, r1, F);
+            if (q + 1 < Q) tmem_ld_spectrum_raw(tm + (uint32_t)((q + 1) * 32), r0, r1);
+            const double2* kb = bk.acquire(q == 0) + t;
+#pragma unroll
+            for (int e = 0; e < 8; e++) cmac(lo[e], F[e], BK::load(kb + e * 64));             // tgsw.jl:128
+#pragma unroll
+            for (int e = 0; e < 8; e++) cmac(hi[e], F[e], BK::load(kb + (8 + e) * 64));
+            bk.release();
+        }
+        fft512_inverse_dual(lo, hi, w, X1, X1 + kSpectrum, X2, t, bar_id);
+        int32_t* p = acc + c2 * kN;
+#pragma unroll
+        for (int m = 0; m < 8; m++) {                                                          // polynomials.jl:115-116, bootstrap.jl:22
+            const int j = t + 64 * m;
+            p[j] = (int32_t)((uint32_t)p[j] + round_to_u32_fast<true>(lo[m].x) + (round_to_u32_fast<true>(hi[m].x) << 16));
+            p[j + 512] = (int32_t)((uint32_t)p[j + 512] + round_to_u32_fast<true>(-lo[m].y) + (round_to_u32_fast<true>(-hi[m].y) << 16));
+        }
+    }
+    group_sync(bar_id);   // the updated accumulator is visible to the whole group before the next rotation reads it
+}
+
 template <int L, int BGBIT, int SYNC, int PROBE, class BK, class W>
 __device__ __forceinline__ void extern_product_step_os(int32_t* acc, int abar, BK& bk, const W& w, double2* X1, double2* X2,
                                                        uint32_t tm, int t, int bar_id, long long (&pr)[4]) {
@@ -510,7 +566,7 @@ __host__ __device__ constexpr int br_tmem_cols(int NP, int G, int L = 2, int TM 
     return c;
 }
 
-// OPT: bit 3 = clock64 phase probe (development; TM == 3 only; writes A.probe);
+// OPT: bit 3 = clock64 phase probe (development; TM == 3 only; writes A.probe); bit 4 = transforms in pairs (TM == 3, l = 2);
 //      bit 7 = a dedicated producer warp walks the key ring and the compute warps only consume.  The CTA then has a
 //      third warpgroup (384 threads are launched with 168 registers each); it hands its registers back
 //      (setmaxnreg.dec 24) and the two compute warpgroups grow to 240 (setmaxnreg.inc), so every sub-partition holds
@@ -610,7 +666,8 @@ __global__ void __launch_bounds__(64 * G + ((OPT >> 7) & 1) * 128, 1) blind_rota
     if (PROBE) t_start = clock64();
 #pragma unroll 1
     for (int i = 0; i < A.n_iter; i++) {   // bootstrap.jl:19-23
-        if constexpr (TM == 3) extern_product_step_os<L, BGBIT, 1, PROBE>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id, pr);
+        if constexpr (TM == 3 && ((OPT >> 4) & 1) && L == 2) extern_product_step_os_dual<BGBIT>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id);
+        else if constexpr (TM == 3) extern_product_step_os<L, BGBIT, 1, PROBE>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id, pr);
         else if constexpr (TM != 0) extern_product_step_tmem<L, BGBIT, NP, (TM == 2 && NP == 2) ? 1 : 0>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id);
         else extern_product_step<L, BGBIT, NP, true, true>(acc, bara[i], bk, w, X1, X2, t, bar_id);
     }

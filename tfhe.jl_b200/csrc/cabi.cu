@@ -139,6 +139,7 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
             case 304:
                 if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3>(ctx, A, s);
                 else return launch_br_g<L, BGBIT, NP, 4, 6, MODE>(ctx, A, s);
+            case 384: if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 128>(ctx, A, s); else break;        // default without the paired transforms
             case 1304:                                                                  // clock64 phase probe of the default kernel
                 if constexpr (NP == 2 && L == 2 && MODE == 0) {
                     BlindRotateArgs B = A;
@@ -177,8 +178,9 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
                     }
                     if (A.count <= sms) return launch_br_g<L, BGBIT, NP, 1, 6, MODE, TMv>(ctx, A, s);
                     if (A.count <= 2 * sms) return launch_br_g<L, BGBIT, NP, 2, 6, MODE, TMv>(ctx, A, s);
-                    // two pieces: output-stationary step + dedicated producer warpgroup (profiles/r2: 486 vs 563 ms per 65 536 gates)
-                    if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 128>(ctx, A, s);
+                    // two pieces: output-stationary step + dedicated producer warpgroup + transforms in pairs where l = 2
+                    // (profiles/r2/k3_variants.md: 480 vs 563 ms per 65 536 gates)
+                    if constexpr (NP == 2) return launch_br_g<L, BGBIT, NP, 4, 5, MODE, 3, 128 | 16>(ctx, A, s);
                     else return launch_br_g<L, BGBIT, NP, 4, 6, MODE, 0, 128>(ctx, A, s);   // one piece: register accumulators + producer warpgroup
                 }
         }

@@ -235,6 +235,104 @@ __device__ __forceinline__ void fft512_inverse(double2 (&a)[8], const W& w, doub
     fft512_inverse_t<0>(a, w, X1, X2, t, bar_id);
 }
 
+// Two transforms per thread in one instruction stream (A through X1a, B through X1b, the tile-local second exchange of
+// both through the one X2 buffer, one after the other).  The arithmetic of one transform is independent of the other's
+// exchanges, so the scheduler can cover the shared-memory latency of A with butterflies of B inside a single warp.
+// Both X1 buffers are in use in every call, so the call opens with a group barrier (every thread has finished the X1
+// loads of the previous call) — two barriers per pair = one per transform, as in the SYNC == 1 single transforms.
+template <class W>
+__device__ __forceinline__ void fft512_forward_dual(double2 (&a)[8], double2 (&b)[8], const W& w, double2* X1a, double2* X1b,
+                                                    double2* X2, int t, int bar_id) {
+#pragma unroll
+    for (int m = 1; m < 8; m++) {
+        a[m] = cmul(a[m], make_double2(kTwistRe[m], kTwistIm[m]));
+        b[m] = cmul(b[m], make_double2(kTwistRe[m], kTwistIm[m]));
+    }
+    dft8<false>(a); dft8<false>(b);
+    {
+        double2 T[8];
+        pass1_twiddles(w, T);
+#pragma unroll
+        for (int q = 0; q < 8; q++) { a[q] = cmul(a[q], T[q]); b[q] = cmul(b[q], T[q]); }
+    }
+    group_sync(bar_id);
+#pragma unroll
+    for (int q = 0; q < 8; q++) { X1a[q * 64 + t] = a[q]; X1b[q * 64 + t] = b[q]; }
+    group_sync(bar_id);
+    const int lo = t & 7, hi = t >> 3;
+#pragma unroll
+    for (int t2 = 0; t2 < 8; t2++) { a[t2] = X1a[hi * 64 + lo + 8 * t2]; b[t2] = X1b[hi * 64 + lo + 8 * t2]; }
+    double2 V[8];
+    pass2_twiddles(w, V);
+    dft8<false>(a);
+#pragma unroll
+    for (int q = 1; q < 8; q++) a[q] = cmul(a[q], V[q]);
+    __syncwarp();
+#pragma unroll
+    for (int q2 = 0; q2 < 8; q2++) X2[hi * 72 + q2 * 9 + lo] = a[q2];
+    __syncwarp();
+#pragma unroll
+    for (int t1 = 0; t1 < 8; t1++) a[t1] = X2[hi * 72 + lo * 9 + t1];
+    dft8<false>(b);
+#pragma unroll
+    for (int q = 1; q < 8; q++) b[q] = cmul(b[q], V[q]);
+    __syncwarp();
+#pragma unroll
+    for (int q2 = 0; q2 < 8; q2++) X2[hi * 72 + q2 * 9 + lo] = b[q2];
+    __syncwarp();
+#pragma unroll
+    for (int t1 = 0; t1 < 8; t1++) b[t1] = X2[hi * 72 + lo * 9 + t1];
+    dft8<false>(a); dft8<false>(b);
+}
+
+template <class W>
+__device__ __forceinline__ void fft512_inverse_dual(double2 (&a)[8], double2 (&b)[8], const W& w, double2* X1a, double2* X1b,
+                                                    double2* X2, int t, int bar_id) {
+    const int lo = t & 7, hi = t >> 3;
+    double2 V[8];
+    pass2_twiddles(w, V);
+    dft8<true>(a);
+#pragma unroll
+    for (int q = 1; q < 8; q++) a[q] = cmulc(a[q], V[q]);
+    __syncwarp();
+#pragma unroll
+    for (int t1 = 0; t1 < 8; t1++) X2[hi * 72 + lo * 9 + t1] = a[t1];
+    __syncwarp();
+#pragma unroll
+    for (int q2 = 0; q2 < 8; q2++) a[q2] = X2[hi * 72 + q2 * 9 + lo];
+    dft8<true>(b);
+#pragma unroll
+    for (int q = 1; q < 8; q++) b[q] = cmulc(b[q], V[q]);
+    __syncwarp();
+#pragma unroll
+    for (int t1 = 0; t1 < 8; t1++) X2[hi * 72 + lo * 9 + t1] = b[t1];
+    __syncwarp();
+#pragma unroll
+    for (int q2 = 0; q2 < 8; q2++) b[q2] = X2[hi * 72 + q2 * 9 + lo];
+    dft8<true>(a); dft8<true>(b);
+    group_sync(bar_id);
+#pragma unroll
+    for (int t2 = 0; t2 < 8; t2++) { X1a[hi * 64 + lo + 8 * t2] = a[t2]; X1b[hi * 64 + lo + 8 * t2] = b[t2]; }
+    group_sync(bar_id);
+#pragma unroll
+    for (int q = 0; q < 8; q++) { a[q] = X1a[q * 64 + t]; b[q] = X1b[q * 64 + t]; }
+    {
+        double2 T[8];
+        pass1_twiddles(w, T);
+#pragma unroll
+        for (int q = 0; q < 8; q++) { a[q] = cmulc(a[q], T[q]); b[q] = cmulc(b[q], T[q]); }
+    }
+    dft8<true>(a); dft8<true>(b);
+    constexpr double sc = 1.0 / 512.0;
+    a[0] = make_double2(a[0].x * sc, a[0].y * sc);
+    b[0] = make_double2(b[0].x * sc, b[0].y * sc);
+#pragma unroll
+    for (int m = 1; m < 8; m++) {
+        a[m] = cmulc(a[m], make_double2(kTwistRe[m] * sc, kTwistIm[m] * sc));
+        b[m] = cmulc(b[m], make_double2(kTwistRe[m] * sc, kTwistIm[m] * sc));
+    }
+}
+
 // round-to-nearest-even to a 64-bit integer, keep the low 32 bits (polynomials.jl:115-116)
 __device__ __forceinline__ uint32_t round_to_u32(double x) { return (uint32_t)(unsigned long long)__double2ll_rn(x); }
 
