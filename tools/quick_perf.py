@@ -15,7 +15,7 @@ def main():
     rng = O.Rng(1)
     base = 256
     bits = np.random.default_rng(0).integers(0, 2, (base, 2)).astype(bool)
-    x = np.tile(O.encrypt(rng, keys, bits[:, 0]), (B // base, 1)); y = np.tile(O.encrypt(rng, keys, bits[:, 1]), (B // base, 1))
+    x = np.tile(O.encrypt(rng, keys, bits[:, 0]), (max(1, B // base), 1)); y = np.tile(O.encrypt(rng, keys, bits[:, 1]), (max(1, B // base), 1))
     dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
     out = torch.empty_like(dx); u = torch.empty((B, 1025), dtype=torch.int32, device="cuda")
     s = torch.cuda.current_stream().cuda_stream
