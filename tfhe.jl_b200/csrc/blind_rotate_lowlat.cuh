@@ -170,204 +170,4 @@ __global__ void __launch_bounds__(64 * 2 * L, 1) blind_rotate_lowlat_kernel(Blin
     if (threadIdx.x == 0) out[kN] = acc[kN];
 }
 
-// ---- K3L2: the l = 2 latency kernel with the spectrum MACs taken off the shared-memory pipe --------------------------
-//
-// In the kernel above the MAC phase of an iteration is bound by shared-memory bandwidth: 4 output groups x (4 F + 4 key
-// spectra) x 8 KB = 256 KB at 128 B/clk = 2 k of the 6.8 k cycles of an iteration (clock64 probe).  Here
-//   * a group's OWN spectrum F_q stays in its registers through barrier A,
-//   * the spectrum of the group that shares its tensor-memory lanes (warps w and w+4 address the same 32 lanes, so group
-//     g pairs with g ^ 2; thread t of one is thread t of the other) comes through TMEM: tcgen05.st before the barrier,
-//     tcgen05.ld after it, on a datapath of its own,
-//   * KT = 1: the key spectra do not pass through shared memory at all.  Every thread reads exactly the key elements it
-//     will multiply (K[e*64 + t]) with coalesced 16-byte read-only loads, one spectrum (8 loads) at a time, issued at the
-//     start of a phase of the PREVIOUS part of the iteration (inverse transform / accumulator update / forward
-//     transform) and parked in the thread's own TMEM row at the end of that phase; the fourth spectrum is consumed
-//     straight from the registers it was loaded into.  KT = 0 keeps the TMA ring of the kernel above.
-// Left for shared memory: two F spectra per output group (64 KB per iteration instead of 256 KB).  Same transforms, same
-// summation order over q, same rounding: bit-identical to K3 and K3L.
-template <int NP, int KT> __host__ __device__ constexpr size_t br_lowlat2_smem_bytes(int n_pad) {
-    return (KT ? (size_t)0 : (size_t)(2 * NP) * 4 * kSpectrum * 16 + 256)   // KT = 0: key slots [output][q] + mbarriers
-           + (size_t)4 * (kSpectrum + kX2Elems) * 16                       // X1, X2 per group
-           + 2 * kN * 4 + (size_t)n_pad * 4;                                // accumulator, modulus-switched mask
-}
-
-template <int BGBIT, int NP, int KT, int PROBE = 0>
-__global__ void __launch_bounds__(256, 1) blind_rotate_lowlat2_kernel(BlindRotateArgs A) {
-    constexpr int L = 2, NG = 4, NO = 2 * NP;
-    constexpr uint32_t offset = decomp_offset<L, BGBIT>();
-    constexpr int kTmemCols = KT ? 256 : 64;   // [0,64): F of the lower / upper group of a lane pair; [64,256): 2 x 3 key slots
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ uint32_t s_tmem_base;
-    constexpr size_t key_bytes = KT ? 0 : (size_t)NO * NG * kSpectrum * 16 + 256;
-    double2* keys = reinterpret_cast<double2*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (KT ? 0 : (size_t)NO * NG * kSpectrum * 16));   // [output][q]
-    double2* xbuf = reinterpret_cast<double2*>(smem_raw + key_bytes);
-    int32_t* acc = reinterpret_cast<int32_t*>(xbuf + (size_t)NG * (kSpectrum + kX2Elems));
-    int32_t* bara = acc + 2 * kN;
-
-    const int t = threadIdx.x & 63, grp = threadIdx.x >> 6, warp = threadIdx.x >> 5;
-    const int bar_id = grp + 1;
-    double2* X1 = xbuf + (size_t)grp * (kSpectrum + kX2Elems);
-    double2* X2 = X1 + kSpectrum;
-    const unsigned long long g = blockIdx.x;
-    Twiddles w; w.load(A.E, t);
-
-    const bool outg = grp < NO;                         // this group also owns an output spectrum
-    const int c2 = grp / NP, pc = grp % NP;             // ... namely (c2, pc): reads BK[i][r][c][c2][pc] for q = (c, r)
-    auto key_ptr = [&](int i, int q) {
-        const int c = q / L, r = q % L;
-        return A.bk_fft + ((((size_t)i * L + r) * 2 + c) * 2 * NP + (size_t)c2 * NP + pc) * kSpectrum + t;
-    };
-    auto issue_keys = [&](int i) {   // KT = 0: the four spectra of iteration i into this output group's slots
-        for (int q = 0; q < NG; q++) {
-            mbar_arrive_expect_tx(full + grp * NG + q, (uint32_t)(kSpectrum * 16));
-            bulk_copy_g2s(keys + ((size_t)grp * NG + q) * kSpectrum, key_ptr(i, q) - t, kSpectrum * 16, full + grp * NG + q);
-        }
-    };
-    if (!KT && threadIdx.x < NO * NG) mbar_init(full + threadIdx.x, 1);
-    if (!KT && threadIdx.x == 0) mbar_fence_init();
-    if (warp == 0) tmem_alloc<kTmemCols>(&s_tmem_base);
-    tmem_fence_before_sync();
-    __syncthreads();
-    tmem_fence_after_sync();
-    const uint32_t tm = s_tmem_base + ((uint32_t)(32 * (warp & 3)) << 16);
-    const uint32_t tm_own = tm + (uint32_t)((grp >> 1) * 32), tm_peer = tm + (uint32_t)(((grp >> 1) ^ 1) * 32);
-    const uint32_t tm_key = tm + 64u + (uint32_t)((grp >> 1) * 96);
-    if (!KT && outg && t == 0) issue_keys(0);
-
-    double2 kq[8];   // KT = 1: the key spectrum in flight from L2
-    auto key_load = [&](int i, int q) {
-        const double2* src = key_ptr(i, q);
-#pragma unroll
-        for (int e = 0; e < 8; e++)   // volatile: issued HERE, a phase ahead of its use, not sunk to the use by the compiler
-            asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(kq[e].x), "=d"(kq[e].y) : "l"(src + e * 64));
-    };
-    if (KT && outg) {
-        key_load(0, 0);
-        tmem_store_spectrum(tm_key, kq);
-        key_load(0, 1);
-    }
-
-    lowlat_prologue(A, g, acc, bara);
-    __syncthreads();
-
-    const int c1 = grp / L, r1 = grp % L;   // phase-1 role
-    const int32_t* p = acc + c1 * kN;
-    long long pr[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ck = 0;   // PROBE: cycles per phase (rotate, forward, A, MAC, B, inverse, update, C)
-    auto lap = [&](int k) { if (PROBE) { const long long n = clock64(); pr[k] += n - ck; ck = n; } };
-#pragma unroll 1
-    for (int i = 0; i < A.n_iter; i++) {   // bootstrap.jl:19-23; a zero rotation is executed (exact no-op)
-        const int s = bara[i] & 2047;
-        if (PROBE) ck = clock64();
-        double2 a[8];
-#pragma unroll
-        for (int m = 0; m < 8; m++) {
-            const int j = t + 64 * m;
-            const uint32_t tl = (uint32_t)rot_coeff(p, j, s) - (uint32_t)p[j] + offset;              // bootstrap.jl:21
-            const uint32_t th = (uint32_t)rot_coeff(p, j + 512, s) - (uint32_t)p[j + 512] + offset;
-            a[m] = make_double2(digit_f64<BGBIT>(tl, r1), -digit_f64<BGBIT>(th, r1));                // tgsw.jl:104-116
-        }
-        lap(0);
-        if (KT && outg) { tmem_store_spectrum(tm_key + 32, kq); key_load(i, 2); }   // q = 1 parked, q = 2 in flight behind the transform
-        fft512_forward(a, w, X1, X2, t, bar_id);
-        if (KT && outg) { tmem_store_spectrum(tm_key + 64, kq); key_load(i, 3); }   // q = 3 stays in registers
-#pragma unroll
-        for (int e = 0; e < 8; e++) X1[e * 64 + t] = a[e];   // X1 is free: every thread of the group passed the 2nd barrier
-        tmem_store_spectrum(tm_own, a);
-        tmem_wait_st();
-        tmem_fence_before_sync();
-        lap(1);
-        __syncthreads();   // A: all spectra published, all reads of acc done
-        tmem_fence_after_sync();
-        lap(2);
-        double2 o[8];
-        if (outg) {
-            int pr0[16], pr1[16], kr0[16], kr1[16];
-            double2 P[8];
-            tmem_ld_spectrum_raw(tm_peer, pr0, pr1);
-            if (KT) tmem_ld_spectrum_raw(tm_key, kr0, kr1);
-            tmem_ld_spectrum_finish(pr0, pr1, P);
-#pragma unroll
-            for (int e = 0; e < 8; e++) o[e] = make_double2(0.0, 0.0);
-#pragma unroll
-            for (int q = 0; q < NG; q++) {   // same summation order as K3: c outer, r inner
-                double2 K[8];
-                if (KT) {
-                    if (q < 3) {
-                        if (q == 0) {   // landed with the peer spectrum (one wait covers every outstanding load)
-#pragma unroll
-                            for (int x = 0; x < 16; x++) asm volatile("" : "+r"(kr0[x]), "+r"(kr1[x]));
-#pragma unroll
-                            for (int x = 0; x < 4; x++) {
-                                K[x] = make_double2(__hiloint2double(kr0[4 * x + 1], kr0[4 * x]), __hiloint2double(kr0[4 * x + 3], kr0[4 * x + 2]));
-                                K[4 + x] = make_double2(__hiloint2double(kr1[4 * x + 1], kr1[4 * x]), __hiloint2double(kr1[4 * x + 3], kr1[4 * x + 2]));
-                            }
-                        } else tmem_ld_spectrum_finish(kr0, kr1, K);
-                        if (q < 2) tmem_ld_spectrum_raw(tm_key + (uint32_t)((q + 1) * 32), kr0, kr1);   // in flight behind this MAC
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 8; e++) K[e] = kq[e];
-                    }
-                } else {
-                    mbar_wait(full + grp * NG + q, (uint32_t)i & 1u);
-                    const double2* Ks = keys + ((size_t)grp * NG + q) * kSpectrum + t;
-#pragma unroll
-                    for (int e = 0; e < 8; e++) K[e] = Ks[e * 64];
-                }
-                if (q == grp) {
-#pragma unroll
-                    for (int e = 0; e < 8; e++) cmac(o[e], a[e], K[e]);                                  // tgsw.jl:128
-                } else if (q == (grp ^ 2)) {
-#pragma unroll
-                    for (int e = 0; e < 8; e++) cmac(o[e], P[e], K[e]);
-                } else {
-                    const double2* F = xbuf + (size_t)q * (kSpectrum + kX2Elems) + t;
-#pragma unroll
-                    for (int e = 0; e < 8; e++) cmac(o[e], F[e * 64], K[e]);
-                }
-            }
-        }
-        tmem_fence_before_sync();
-        lap(3);
-        __syncthreads();   // B: spectra (shared memory and TMEM) and key slots consumed
-        tmem_fence_after_sync();
-        lap(4);
-        if (outg) {
-            const bool more = i + 1 < A.n_iter;
-            if (!KT && t == 0 && more) issue_keys(i + 1);   // lands during the inverse + next forward transform
-            if (KT && more) key_load(i + 1, 0);
-            fft512_inverse(o, w, X1, X2, t, bar_id);
-            if (KT && more) { tmem_store_spectrum(tm_key, kq); key_load(i + 1, 1); }
-            lap(5);
-            int32_t* pa = acc + c2 * kN;
-#pragma unroll
-            for (int m = 0; m < 8; m++) {
-                uint32_t vl = round_to_u32_fast<NP == 2>(o[m].x), vh = round_to_u32_fast<NP == 2>(-o[m].y);   // polynomials.jl:115-116
-                if (pc == 1) { vl <<= 16; vh <<= 16; }
-                const int j = t + 64 * m;
-                if (NP == 1) {
-                    pa[j] = (int32_t)((uint32_t)pa[j] + vl);                                              // bootstrap.jl:22
-                    pa[j + 512] = (int32_t)((uint32_t)pa[j + 512] + vh);
-                } else {
-                    atomicAdd(reinterpret_cast<unsigned int*>(pa + j), vl);
-                    atomicAdd(reinterpret_cast<unsigned int*>(pa + j + 512), vh);
-                }
-            }
-        }
-        lap(6);
-        __syncthreads();   // C: accumulator updated
-        lap(7);
-    }
-    if (PROBE && A.probe && blockIdx.x == 0 && (threadIdx.x & 31) == 0)
-        for (int k = 0; k < 8; k++) A.probe[warp * 8 + k] = (unsigned long long)pr[k];
-
-    // tlwe_extract_sample (tlwe.jl:55-59): a = (p_0, -p_{N-1}, ..., -p_1), b = acc_b[0]
-    int32_t* out = A.out + g * (kN + 1);
-    for (int x = threadIdx.x; x < kN; x += blockDim.x) out[x] = x == 0 ? acc[0] : (int32_t)(0u - (uint32_t)acc[kN - x]);
-    if (threadIdx.x == 0) out[kN] = acc[kN];
-    tmem_fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc<kTmemCols>(s_tmem_base);
-}
-
 }  // namespace tfhe_b200

@@ -166,46 +166,6 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
                     const unsigned long long sms = (unsigned long long)ctx->sm_count;
                     // measured (tools/latency_probe.py): one wave of 148 gates takes 1.95 ms on the latency kernel,
                     // 592 gates 6.45 ms on the 4-gates-per-CTA kernel, so up to 3 waves the latency kernel also wins
-                    if constexpr (L == 2) {
-                        // l = 2: own / lane-peer spectra from registers / TMEM; lowlat = 3: key spectra through TMEM as well
-                        if (A.count <= 3 * sms && ctx->lowlat >= 2) {
-                            auto launch2 = [&](auto kern, size_t smem) -> int {
-                                CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                                kern<<<(unsigned)A.count, 256, smem, s>>>(A);
-                                CU(cudaGetLastError());
-                                ctx->launches++;
-                                return 0;
-                            };
-                            if constexpr (NP == 2 && MODE == 0) {
-                                if (ctx->lowlat == 12 || ctx->lowlat == 13) {   // clock64 phase probe (development)
-                                    BlindRotateArgs B = A;
-                                    CU(cudaMalloc(&B.probe, 8 * 8 * sizeof(unsigned long long)));
-                                    auto launchp = [&](auto kern, size_t smem) -> int {
-                                        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                                        kern<<<(unsigned)A.count, 256, smem, s>>>(B);
-                                        CU(cudaGetLastError());
-                                        ctx->launches++;
-                                        return 0;
-                                    };
-                                    int rc = ctx->lowlat == 12 ? launchp(blind_rotate_lowlat2_kernel<BGBIT, NP, 0, 1>, br_lowlat2_smem_bytes<NP, 0>(A.n_pad))
-                                                               : launchp(blind_rotate_lowlat2_kernel<BGBIT, NP, 1, 1>, br_lowlat2_smem_bytes<NP, 1>(A.n_pad));
-                                    std::vector<unsigned long long> h(8 * 8);
-                                    CU(cudaStreamSynchronize(s));
-                                    CU(cudaMemcpy(h.data(), B.probe, h.size() * 8, cudaMemcpyDeviceToHost));
-                                    CU(cudaFree(B.probe));
-                                    for (int w = 0; w < 8; w++) {
-                                        const unsigned long long* o = &h[w * 8];
-                                        fprintf(stderr, "lowlat2 probe warp %d (cycles per iteration): rotate %.0f fwd %.0f barA %.0f mac %.0f barB %.0f inv %.0f update %.0f barC %.0f\n", w,
-                                                (double)o[0] / A.n_iter, (double)o[1] / A.n_iter, (double)o[2] / A.n_iter, (double)o[3] / A.n_iter,
-                                                (double)o[4] / A.n_iter, (double)o[5] / A.n_iter, (double)o[6] / A.n_iter, (double)o[7] / A.n_iter);
-                                    }
-                                    return rc;
-                                }
-                            }
-                            if (ctx->lowlat == 2) return launch2(blind_rotate_lowlat2_kernel<BGBIT, NP, 0>, br_lowlat2_smem_bytes<NP, 0>(A.n_pad));
-                            return launch2(blind_rotate_lowlat2_kernel<BGBIT, NP, 1>, br_lowlat2_smem_bytes<NP, 1>(A.n_pad));
-                        }
-                    }
                     if (A.count <= 3 * sms && ctx->lowlat && br_lowlat_smem_bytes<L, NP>(A.n_pad) <= 227 * 1024) {
                         // latency path (blind_rotate_lowlat.cuh): one gate per CTA, one digit polynomial per group
                         auto kern = blind_rotate_lowlat_kernel<L, BGBIT, NP>;
