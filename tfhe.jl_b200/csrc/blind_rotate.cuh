@@ -64,6 +64,14 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gm
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// the same with an L2 eviction policy for the lines it touches
+__device__ __forceinline__ void bulk_copy_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
 
 constexpr int kChunkElems = 2 * kSpectrum;        // double2 per key chunk
 constexpr int kChunkBytes = kChunkElems * 16;     // 16 KB
@@ -95,6 +103,7 @@ template <int L, int NP, int STAGES, int ORDER = 0, int PROBE = 0, int PW = 0> s
     // position (iteration, index in the iteration)) — advanced incrementally, no division in the loop
     int iss = 0, iss_stage = 0, iss_round = 0, iss_i = 0, iss_q = 0;
     uint32_t ready_next = 0;  // PW: result of the early test of the next chunk's full barrier
+    uint64_t policy = 0;      // != 0: L2 eviction policy of the key lines (the key outlives the ciphertext stream in L2)
 
     // index in the iteration (consumption order) -> chunk inside the stored row: storage order is (r, c, half)
     static __device__ __forceinline__ int stored_index(int q) {
@@ -106,7 +115,8 @@ template <int L, int NP, int STAGES, int ORDER = 0, int PROBE = 0, int PW = 0> s
     __device__ __forceinline__ void issue_next() {
         const size_t off = ((size_t)iss_i * kChunksPerIter + (size_t)stored_index(iss_q)) * kChunkElems;
         mbar_arrive_expect_tx(full + iss_stage, kChunkBytes);
-        bulk_copy_g2s(const_cast<double2*>(ring) + (size_t)iss_stage * kChunkElems, bk + off, kChunkBytes, full + iss_stage);
+        if (policy) bulk_copy_g2s_hint(const_cast<double2*>(ring) + (size_t)iss_stage * kChunkElems, bk + off, kChunkBytes, full + iss_stage, policy);
+        else bulk_copy_g2s(const_cast<double2*>(ring) + (size_t)iss_stage * kChunkElems, bk + off, kChunkBytes, full + iss_stage);
         iss++;
         if (++iss_stage == STAGES) { iss_stage = 0; iss_round++; }
         if (++iss_q == kChunksPerIter) { iss_q = 0; iss_i++; }
@@ -545,6 +555,7 @@ struct BlindRotateArgs {
     int n, n_iter, n_pad;
     unsigned long long count;
     unsigned long long* probe;   // development: clock64 phase probe of the OPT bit-3 kernel variants (else null)
+    int l2_hint;                 // 1: key chunks are fetched with the L2 evict_last policy
 };
 
 // per-group shared memory: X1 + X2 + acc (+ bara, n_pad words)
@@ -609,7 +620,10 @@ __global__ void __launch_bounds__(64 * G + ((OPT >> 7) & 1) * 128, 1) blind_rota
         static_assert(!PWARP || G == 4, "register rebalancing assumes two full compute warpgroups");
         if ((threadIdx.x >> 5) >= 2 * G) {
             asm volatile("setmaxnreg.dec.sync.aligned.u32 24;" ::: "memory");
-            if (threadIdx.x == 64 * G) bk.produce_all();
+            if (threadIdx.x == 64 * G) {
+                if (A.l2_hint) bk.policy = l2_policy_evict_last();
+                bk.produce_all();
+            }
             return;   // the compute warps meet at named barriers only from here on
         }
         asm volatile("setmaxnreg.inc.sync.aligned.u32 240;" ::: "memory");

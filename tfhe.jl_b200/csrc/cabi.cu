@@ -42,6 +42,7 @@ struct tfhe_b200_ctx {
     int NP = 2;
     int G = 0;                       // gates per CTA of the blind-rotation kernel (0 = default, see launch_br_np)
     int sm_count = 148;
+    int l2_hint = 0;                 // TFHE_B200_L2HINT=1: key chunks fetched with the L2 evict_last policy (K3 with the producer warpgroup)
     int lowlat = 1;                  // batches of <= 1 gate per SM: one gate per CTA spread over 4 groups + sliced key switch
     int ks_tile = 1;                 // large batches: tiled key switch (TFHE_B200_KS_TILE=0: one CTA per ciphertext)
     int mk_ring = 1;                 // MK blind rotation: 1 = TMA key ring, several gates per CTA (mk_blind_rotate.cuh)
@@ -294,7 +295,7 @@ bool gate_coeffs(int op, int32_t& cb, int32_t& ka, int32_t& kb) {
 
 BlindRotateArgs br_args(tfhe_b200_ctx* ctx, size_t count) {
     BlindRotateArgs A{};
-    A.bk_fft = ctx->d_bk_fft; A.E = ctx->d_E;
+    A.bk_fft = ctx->d_bk_fft; A.E = ctx->d_E; A.l2_hint = ctx->l2_hint;
     A.n = ctx->P.n; A.n_iter = ctx->P.n; A.n_pad = (ctx->P.n + 3) & ~3;
     A.count = count; A.mu = kMu8;
     return A;
@@ -383,6 +384,7 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
     c->mk_ring = env_int("TFHE_B200_MK_RING", 1);
     c->mk_pw = env_int("TFHE_B200_MK_PW", 1);
     c->lowlat = env_int("TFHE_B200_LOWLAT", 1);
+    c->l2_hint = env_int("TFHE_B200_L2HINT", 0);
     c->ks_tile = env_int("TFHE_B200_KS_TILE", 1);
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) c->sm_count = prop.multiProcessorCount; }
     {   // gates per host-staged chunk: at least one wave of CTAs, never zero or negative
