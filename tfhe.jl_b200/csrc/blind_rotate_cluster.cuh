@@ -1,0 +1,162 @@
+// blind_rotate_cluster.cuh — K3C: blind rotation of ONE gate by a CLUSTER of two CTAs (two SMs), 80-bit set, two pieces.
+//
+// K3L (blind_rotate_lowlat.cuh) runs the four forward and four inverse transforms of an iteration at once on one SM; both
+// phases are bound by that SM's FP64 rate (clock64 probe).  Here CTA c of the pair owns accumulator
+// component c for the whole blind rotation:
+//
+//   phase 1  group r of CTA c: rotate/subtract acc[c] (bootstrap.jl:21), digit r (tgsw.jl:104-116), forward transform;
+//            the spectrum F_(c,r) goes to the CTA's own shared memory AND, with st.async (16 B per store, completing
+//            bytes on an mbarrier of the peer), into a landing buffer of the other CTA         -> CTA barrier A
+//   phase 2  group pc of CTA c owns output (c' = c, piece pc): first the two products with the CTA's own spectra
+//            F_(c,0), F_(c,1) — they run while the peer's 16 KB are in flight (DSMEM moves ~11 B/clk each way,
+//            tools/dsmem_test.cu) —, then, after the landing barrier, the two with the peer's        (tgsw.jl:128)
+//                                                                                              -> CTA barrier B
+//   phase 3  inverse transform, round (polynomials.jl:115-116), high piece << 16, integer atomic add into acc[c]
+//                                                                                              -> CTA barrier C
+//
+// acc[c] never leaves its CTA; the only traffic between the SMs is the spectra, and the only cluster-wide
+// synchronisation is their landing barrier (two landing buffers, used alternately: a CTA can only send the spectra of
+// iteration i+2 after it has consumed the peer's of iteration i+1, which the peer sent after it had finished reading
+// iteration i).  The sum over q is taken own-spectra-first, i.e. in the order (2,3,0,1) in CTA 1: this kernel is only
+// used with the two-piece transform, where every partial sum is an exact integer below 2^53 by the bound of DESIGN.md §4,
+// so the rounded result does not depend on the order and the output is bit-identical to K3 / K3L (tests).
+#pragma once
+#include "blind_rotate_lowlat.cuh"
+
+namespace tfhe_b200 {
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_map(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 16 bytes into the peer's shared memory; the peer's mbarrier counts them
+__device__ __forceinline__ void st_async16(uint32_t remote_addr, double2 v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];"
+                 ::"r"(remote_addr), "l"(__double_as_longlong(v.x)), "l"(__double_as_longlong(v.y)), "r"(remote_bar) : "memory");
+}
+
+constexpr int kClKeySlots = 4;   // all four key spectra of an output are prefetched during the previous iteration
+__host__ __device__ constexpr size_t br_cluster_smem_bytes(int n_pad) {
+    return (size_t)2 * kClKeySlots * kSpectrum * 16   // key slots [output group][q]
+           + (size_t)2 * 2 * kSpectrum * 16           // landing buffers [2][r]
+           + 128                                      // mbarriers: 8 key + 2 landing
+           + (size_t)2 * (kSpectrum + kX2Elems) * 16  // X1, X2 per group
+           + 2 * kN * 4 + (size_t)n_pad * 4;          // accumulator (both components initialised, one maintained), mask
+}
+
+template <int BGBIT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) blind_rotate_cluster_kernel(BlindRotateArgs A) {
+    constexpr int L = 2, NP = 2, NQ = 4;
+    constexpr uint32_t offset = decomp_offset<L, BGBIT>();
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double2* keys = reinterpret_cast<double2*>(smem_raw);                       // [grp][q][512]
+    double2* land = keys + (size_t)2 * kClKeySlots * kSpectrum;                 // [buf][r][512]
+    uint64_t* kbar = reinterpret_cast<uint64_t*>(land + (size_t)4 * kSpectrum); // [grp][q]
+    uint64_t* lbar = kbar + 8;                                                  // [buf]
+    double2* xbuf = reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(kbar) + 128);
+    int32_t* acc = reinterpret_cast<int32_t*>(xbuf + (size_t)2 * (kSpectrum + kX2Elems));
+    int32_t* bara = acc + 2 * kN;
+
+    const int t = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int bar_id = grp + 1;
+    const int c = (int)cluster_ctarank();      // accumulator component of this CTA = output component c'
+    const int peer = c ^ 1;
+    double2* X1 = xbuf + (size_t)grp * (kSpectrum + kX2Elems);
+    double2* X2 = X1 + kSpectrum;
+    const unsigned long long g = blockIdx.x >> 1;
+    TwiddlesFull w; w.load(A.E, t);
+
+    // output group pc = grp reads, for q = (cq, r), the spectrum BK[i][r][cq][c][pc]
+    auto issue_keys = [&](int i) {
+        for (int q = 0; q < NQ; q++) {
+            const int cq = q / L, r = q % L;
+            const double2* src = A.bk_fft + ((((size_t)i * L + r) * 2 + cq) * 2 * NP + (size_t)c * NP + grp) * kSpectrum;
+            mbar_arrive_expect_tx(kbar + grp * kClKeySlots + q, (uint32_t)(kSpectrum * 16));
+            bulk_copy_g2s(keys + ((size_t)grp * kClKeySlots + q) * kSpectrum, src, kSpectrum * 16, kbar + grp * kClKeySlots + q);
+        }
+    };
+    if (threadIdx.x < 10) mbar_init(kbar + threadIdx.x, 1);   // 8 key + 2 landing barriers, contiguous
+    if (threadIdx.x == 0) mbar_fence_init();
+    __syncthreads();
+    if (t == 0) issue_keys(0);
+    lowlat_prologue(A, g, acc, bara);
+    cluster_sync_all();   // both CTAs' barriers are initialised before the first remote store can arrive (also a CTA barrier)
+
+    const uint32_t r_land = cluster_map(smem_u32(land), (uint32_t)peer), r_lbar = cluster_map(smem_u32(lbar), (uint32_t)peer);
+    int32_t* p = acc + c * kN;
+    const int q_own = c * L + grp, q_sib = c * L + (grp ^ 1);
+#pragma unroll 1
+    for (int i = 0; i < A.n_iter; i++) {   // bootstrap.jl:19-23; a zero rotation is executed (exact no-op)
+        const int s = bara[i] & 2047;
+        const int buf = i & 1;
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(lbar + buf, (uint32_t)(2 * kSpectrum * 16));   // the peer's two spectra
+        double2 a[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            const int j = t + 64 * m;
+            const uint32_t tl = (uint32_t)rot_coeff(p, j, s) - (uint32_t)p[j] + offset;              // bootstrap.jl:21
+            const uint32_t th = (uint32_t)rot_coeff(p, j + 512, s) - (uint32_t)p[j + 512] + offset;
+            a[m] = make_double2(digit_f64<BGBIT>(tl, grp), -digit_f64<BGBIT>(th, grp));              // tgsw.jl:104-116
+        }
+        fft512_forward(a, w, X1, X2, t, bar_id);
+        {
+            const uint32_t dst = r_land + (uint32_t)(((buf * 2 + grp) * kSpectrum + t) * 16);
+#pragma unroll
+            for (int e = 0; e < 8; e++) st_async16(dst + (uint32_t)(e * 64 * 16), a[e], r_lbar + (uint32_t)(buf * 8));
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) X1[e * 64 + t] = a[e];   // X1 is free: every thread of the group passed the 2nd barrier
+        __syncthreads();   // A: the sibling group's spectrum is published, all reads of acc done
+        double2 o[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) o[e] = make_double2(0.0, 0.0);
+        {   // own spectrum from registers
+            mbar_wait(kbar + grp * kClKeySlots + q_own, (uint32_t)i & 1u);
+            const double2* K = keys + ((size_t)grp * kClKeySlots + q_own) * kSpectrum + t;
+#pragma unroll
+            for (int e = 0; e < 8; e++) cmac(o[e], a[e], K[e * 64]);                                  // tgsw.jl:128
+        }
+        {   // the sibling group's
+            mbar_wait(kbar + grp * kClKeySlots + q_sib, (uint32_t)i & 1u);
+            const double2* F = xbuf + (size_t)(grp ^ 1) * (kSpectrum + kX2Elems) + t;
+            const double2* K = keys + ((size_t)grp * kClKeySlots + q_sib) * kSpectrum + t;
+#pragma unroll
+            for (int e = 0; e < 8; e++) cmac(o[e], F[e * 64], K[e * 64]);
+        }
+        mbar_wait(lbar + buf, (uint32_t)(i >> 1) & 1u);   // the peer's spectra have landed
+#pragma unroll
+        for (int r = 0; r < L; r++) {
+            const int q = peer * L + r;
+            mbar_wait(kbar + grp * kClKeySlots + q, (uint32_t)i & 1u);
+            const double2* F = land + (size_t)(buf * 2 + r) * kSpectrum + t;
+            const double2* K = keys + ((size_t)grp * kClKeySlots + q) * kSpectrum + t;
+#pragma unroll
+            for (int e = 0; e < 8; e++) cmac(o[e], F[e * 64], K[e * 64]);
+        }
+        __syncthreads();   // B: published spectra and key slots consumed
+        if (t == 0 && i + 1 < A.n_iter) issue_keys(i + 1);   // lands during the inverse + next forward transform
+        fft512_inverse(o, w, X1, X2, t, bar_id);
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            uint32_t vl = round_to_u32_fast<true>(o[m].x), vh = round_to_u32_fast<true>(-o[m].y);   // polynomials.jl:115-116
+            if (grp == 1) { vl <<= 16; vh <<= 16; }
+            const int j = t + 64 * m;
+            atomicAdd(reinterpret_cast<unsigned int*>(p + j), vl);                                   // bootstrap.jl:22
+            atomicAdd(reinterpret_cast<unsigned int*>(p + j + 512), vh);
+        }
+        __syncthreads();   // C: accumulator updated
+    }
+
+    // tlwe_extract_sample (tlwe.jl:55-59): a = (p_0, -p_{N-1}, ..., -p_1) from component 0, b = acc_b[0] from component 1
+    int32_t* out = A.out + g * (kN + 1);
+    if (c == 0) {
+        for (int x = threadIdx.x; x < kN; x += blockDim.x) out[x] = x == 0 ? p[0] : (int32_t)(0u - (uint32_t)p[kN - x]);
+    } else if (threadIdx.x == 0) out[kN] = p[0];
+    cluster_sync_all();   // neither CTA leaves while the other could still address its shared memory
+}
+
+}  // namespace tfhe_b200

@@ -17,6 +17,7 @@
 #include "kernels.cuh"
 #include "blind_rotate.cuh"
 #include "blind_rotate_lowlat.cuh"
+#include "blind_rotate_cluster.cuh"
 #include "mk_kernels.cuh"
 #include "mk_blind_rotate.cuh"
 #include "mk_blind_rotate_lowlat.cuh"
@@ -43,6 +44,7 @@ struct tfhe_b200_ctx {
     int G = 0;                       // gates per CTA of the blind-rotation kernel (0 = default, see launch_br_np)
     int sm_count = 148;
     int l2_hint = 0;                 // TFHE_B200_L2HINT=1: key chunks fetched with the L2 evict_last policy (K3 with the producer warpgroup)
+    int cluster = 0;                 // TFHE_B200_CLUSTER=1: batches of <= 1 gate per two SMs take the two-CTA cluster kernel
     int lowlat = 1;                  // batches of <= 1 gate per SM: one gate per CTA spread over 4 groups + sliced key switch
     int ks_tile = 1;                 // large batches: tiled key switch (TFHE_B200_KS_TILE=0: one CTA per ciphertext)
     int mk_ring = 1;                 // MK blind rotation: 1 = TMA key ring, several gates per CTA (mk_blind_rotate.cuh)
@@ -167,6 +169,18 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
                     const unsigned long long sms = (unsigned long long)ctx->sm_count;
                     // measured (tools/latency_probe.py): one wave of 148 gates takes 1.95 ms on the latency kernel,
                     // 592 gates 6.45 ms on the 4-gates-per-CTA kernel, so up to 3 waves the latency kernel also wins
+                    if constexpr (L == 2 && NP == 2) {
+                        // at most one gate per two SMs: a cluster of two CTAs per gate (blind_rotate_cluster.cuh)
+                        if (2 * A.count <= sms && ctx->lowlat && ctx->cluster) {
+                            auto kern = blind_rotate_cluster_kernel<BGBIT>;
+                            const size_t smem = br_cluster_smem_bytes(A.n_pad);
+                            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                            kern<<<(unsigned)(2 * A.count), 128, smem, s>>>(A);
+                            CU(cudaGetLastError());
+                            ctx->launches++;
+                            return 0;
+                        }
+                    }
                     if (A.count <= 3 * sms && ctx->lowlat && br_lowlat_smem_bytes<L, NP>(A.n_pad) <= 227 * 1024) {
                         // latency path (blind_rotate_lowlat.cuh): one gate per CTA, one digit polynomial per group
                         auto kern = blind_rotate_lowlat_kernel<L, BGBIT, NP>;
@@ -385,6 +399,7 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
     c->mk_pw = env_int("TFHE_B200_MK_PW", 1);
     c->lowlat = env_int("TFHE_B200_LOWLAT", 1);
     c->l2_hint = env_int("TFHE_B200_L2HINT", 0);
+    c->cluster = env_int("TFHE_B200_CLUSTER", 0);
     c->ks_tile = env_int("TFHE_B200_KS_TILE", 1);
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) c->sm_count = prop.multiProcessorCount; }
     {   // gates per host-staged chunk: at least one wave of CTAs, never zero or negative
