@@ -241,11 +241,13 @@ def test_api_mirror_truth_tables():
 
 
 @pytest.mark.parametrize("flags", [_cabi.FLAG_SPLIT_FFT, _cabi.FLAG_UNSPLIT_FFT], ids=["split", "unsplit"])
-@pytest.mark.parametrize("count", [3, 148, 149, 444, 445, 601])
+@pytest.mark.parametrize("count", [3, 37, 38, 74, 75, 148, 149, 444, 445, 601])
 def test_every_batch_size_dispatch_path_equals_oracle(keys80_small, octx80_small, flags, count):
-    """The library picks a kernel shape by batch size: up to 3 gates per SM the latency kernel (one gate per CTA
-    spread over 4 groups, 1-3 waves) + sliced key switch, above that four gates per CTA.  With a short LWE key
-    (n = 24) the oracle can check EVERY ciphertext of every path; 445 / 601 leave the last CTA ragged."""
+    """The library picks a kernel shape by batch size: up to one gate per two SMs (two-piece transform) a cluster of two
+    CTAs per gate (37 MUX gates = 74 bootstraps is the last such batch, 74 NAND gates likewise), up to 3 gates per SM
+    the latency kernel (one gate per CTA spread over 4 groups, 1-3 waves) + sliced key switch, above that four gates per
+    CTA.  With a short LWE key (n = 24) the oracle can check EVERY ciphertext of every path; 445 / 601 leave the last
+    CTA ragged."""
     P = keys80_small.params
     ctx = T.Context(n=P.n, l=P.l, bgbit=P.bgbit, t=P.t, basebit=P.basebit, flags=flags)
     ctx.load_bk(keys80_small.bk); ctx.load_ksk(keys80_small.ksk)
@@ -254,6 +256,25 @@ def test_every_batch_size_dispatch_path_equals_oracle(keys80_small, octx80_small
     x, y, z = (O.encrypt(rng, keys80_small, bits[:, i]) for i in range(3))
     assert np.array_equal(ctx.gate(O.NAND, x, y), octx80_small.gate(O.NAND, x, y))
     assert np.array_equal(ctx.gate(O.MUX, x, y, z), octx80_small.gate(O.MUX, x, y, z))
+
+
+def test_cluster_kernel_can_be_disabled_and_agrees(keys80, octx80, gctx80, monkeypatch):
+    """Full-size key (n = 500): the two-CTA cluster kernel (default for <= 74 bootstraps), the one-CTA latency kernel
+    (TFHE_B200_CLUSTER=0) and the oracle give the same ciphertexts, for a plain gate and for MUX (two bootstraps per gate
+    in one launch)."""
+    rng = O.Rng(22)
+    bits = np.random.default_rng(22).integers(0, 2, (20, 3)).astype(bool)
+    x, y, z = (O.encrypt(rng, keys80, bits[:, i]) for i in range(3))
+    got_nand, got_mux = gctx80.gate(O.NAND, x, y), gctx80.gate(O.MUX, x, y, z)
+    monkeypatch.setenv("TFHE_B200_CLUSTER", "0")
+    P = keys80.params
+    ctx = T.Context(n=P.n, l=P.l, bgbit=P.bgbit, t=P.t, basebit=P.basebit)
+    ctx.load_bk(keys80.bk); ctx.load_ksk(keys80.ksk)
+    assert np.array_equal(got_nand, ctx.gate(O.NAND, x, y))
+    assert np.array_equal(got_mux, ctx.gate(O.MUX, x, y, z))
+    assert np.array_equal(got_nand[:4], octx80.gate(O.NAND, x[:4], y[:4]))
+    assert np.array_equal(got_mux[:2], octx80.gate(O.MUX, x[:2], y[:2], z[:2]))
+    assert np.array_equal(O.decrypt(keys80, got_mux), np.where(bits[:, 0], bits[:, 1], bits[:, 2]))
 
 
 def test_latency_path_can_be_disabled_and_agrees(keys80, gctx80, monkeypatch):

@@ -14,6 +14,12 @@
 //   phase 3  inverse transform, round (polynomials.jl:115-116), high piece << 16, integer atomic add into acc[c]
 //                                                                                              -> CTA barrier C
 //
+// Key: the four spectra BK[i][r][cq][c'=c][pc] of an output are copied (TMA bulk copies, one mbarrier per group) into one of
+// TWO sets of slots, the set of iteration i+1 right after barrier A of iteration i: a 64 KB fill shares the shared-memory
+// pipe with whatever runs beside it and was measured to lengthen a transform phase by ~700 cycles, while in the window
+// after barrier A the warps sit behind their remote stores anyway (clock64 probe: 1.276 -> 1.111 ms).  Reading the key
+// straight into registers instead (coalesced 16-byte loads, a phase ahead) was slower (1.38 ms).
+//
 // acc[c] never leaves its CTA; the only traffic between the SMs is the spectra, and the only cluster-wide
 // synchronisation is their landing barrier (two landing buffers, used alternately: a CTA can only send the spectra of
 // iteration i+2 after it has consumed the peer's of iteration i+1, which the peer sent after it had finished reading
@@ -39,24 +45,25 @@ __device__ __forceinline__ void st_async16(uint32_t remote_addr, double2 v, uint
                  ::"r"(remote_addr), "l"(__double_as_longlong(v.x)), "l"(__double_as_longlong(v.y)), "r"(remote_bar) : "memory");
 }
 
+constexpr int kClThreads = 128;  // two 64-thread groups
 constexpr int kClKeySlots = 4;   // all four key spectra of an output are prefetched during the previous iteration
 __host__ __device__ constexpr size_t br_cluster_smem_bytes(int n_pad) {
-    return (size_t)2 * kClKeySlots * kSpectrum * 16   // key slots [output group][q]
+    return (size_t)2 * 2 * kClKeySlots * kSpectrum * 16   // key slots [buffer][output group][q], used alternately
            + (size_t)2 * 2 * kSpectrum * 16           // landing buffers [2][r]
-           + 128                                      // mbarriers: 8 key + 2 landing
+           + 128                                      // mbarriers: 2 x 2 key + 2 landing
            + (size_t)2 * (kSpectrum + kX2Elems) * 16  // X1, X2 per group
            + 2 * kN * 4 + (size_t)n_pad * 4;          // accumulator (both components initialised, one maintained), mask
 }
 
-template <int BGBIT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) blind_rotate_cluster_kernel(BlindRotateArgs A) {
+template <int BGBIT, int PROBE = 0>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kClThreads, 1) blind_rotate_cluster_kernel(BlindRotateArgs A) {
     constexpr int L = 2, NP = 2, NQ = 4;
     constexpr uint32_t offset = decomp_offset<L, BGBIT>();
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double2* keys = reinterpret_cast<double2*>(smem_raw);                       // [grp][q][512]
-    double2* land = keys + (size_t)2 * kClKeySlots * kSpectrum;                 // [buf][r][512]
-    uint64_t* kbar = reinterpret_cast<uint64_t*>(land + (size_t)4 * kSpectrum); // [grp][q]
-    uint64_t* lbar = kbar + 8;                                                  // [buf]
+    double2* keys = reinterpret_cast<double2*>(smem_raw);                       // [buf][grp][q][512]
+    double2* land = keys + (size_t)2 * 2 * kClKeySlots * kSpectrum;             // [buf][r][512]
+    uint64_t* kbar = reinterpret_cast<uint64_t*>(land + (size_t)4 * kSpectrum); // [buf][grp]
+    uint64_t* lbar = kbar + 4;                                                  // [buf]
     double2* xbuf = reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(kbar) + 128);
     int32_t* acc = reinterpret_cast<int32_t*>(xbuf + (size_t)2 * (kSpectrum + kX2Elems));
     int32_t* bara = acc + 2 * kN;
@@ -71,28 +78,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) blind_rotate
     TwiddlesFull w; w.load(A.E, t);
 
     // output group pc = grp reads, for q = (cq, r), the spectrum BK[i][r][cq][c][pc]
-    auto issue_keys = [&](int i) {
-        for (int q = 0; q < NQ; q++) {
-            const int cq = q / L, r = q % L;
+    // One barrier per (slot set, group) counts all four copies of an iteration; lanes 0..3 of the group's first warp issue
+    // one copy each in the same instructions.  (Measured alternatives: both warps of the group issuing two copies each,
+    // and a fifth warp that only issues — 1.146 and 1.122 ms against 1.111 ms: a warp that issues a bulk copy loses
+    // ~350 cycles whatever the number of copies, and the extra warp slows the transforms of its sub-partition.)
+    auto issue_keys = [&](int i) {   // called by the first warp of the group
+        const int kb = i & 1;
+        if (t == 0) mbar_arrive_expect_tx(kbar + kb * 2 + grp, (uint32_t)(NQ * kSpectrum * 16));
+        __syncwarp();
+        if (t < NQ) {
+            const int q = t, cq = q / L, r = q % L;
             const double2* src = A.bk_fft + ((((size_t)i * L + r) * 2 + cq) * 2 * NP + (size_t)c * NP + grp) * kSpectrum;
-            mbar_arrive_expect_tx(kbar + grp * kClKeySlots + q, (uint32_t)(kSpectrum * 16));
-            bulk_copy_g2s(keys + ((size_t)grp * kClKeySlots + q) * kSpectrum, src, kSpectrum * 16, kbar + grp * kClKeySlots + q);
+            bulk_copy_g2s(keys + ((size_t)(kb * 2 + grp) * kClKeySlots + q) * kSpectrum, src, kSpectrum * 16, kbar + kb * 2 + grp);
         }
     };
-    if (threadIdx.x < 10) mbar_init(kbar + threadIdx.x, 1);   // 8 key + 2 landing barriers, contiguous
+    if (threadIdx.x < 6) mbar_init(kbar + threadIdx.x, 1);   // 4 key + 2 landing barriers, contiguous
     if (threadIdx.x == 0) mbar_fence_init();
     __syncthreads();
-    if (t == 0) issue_keys(0);
+    if (t < 32) issue_keys(0);
     lowlat_prologue(A, g, acc, bara);
     cluster_sync_all();   // both CTAs' barriers are initialised before the first remote store can arrive (also a CTA barrier)
 
     const uint32_t r_land = cluster_map(smem_u32(land), (uint32_t)peer), r_lbar = cluster_map(smem_u32(lbar), (uint32_t)peer);
     int32_t* p = acc + c * kN;
     const int q_own = c * L + grp, q_sib = c * L + (grp ^ 1);
+    // PROBE: cycles per phase (rotate, forward, send + publish, barrier A, own products, landing wait, peer products,
+    // barrier B, inverse, update + barrier C)
+    long long pr[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, ck = 0;
+    auto lap = [&](int k) { if (PROBE) { const long long n = clock64(); pr[k] += n - ck; ck = n; } };
 #pragma unroll 1
     for (int i = 0; i < A.n_iter; i++) {   // bootstrap.jl:19-23; a zero rotation is executed (exact no-op)
         const int s = bara[i] & 2047;
         const int buf = i & 1;
+        if (PROBE) ck = clock64();
         if (threadIdx.x == 0) mbar_arrive_expect_tx(lbar + buf, (uint32_t)(2 * kSpectrum * 16));   // the peer's two spectra
         double2 a[8];
 #pragma unroll
@@ -102,7 +120,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) blind_rotate
             const uint32_t th = (uint32_t)rot_coeff(p, j + 512, s) - (uint32_t)p[j + 512] + offset;
             a[m] = make_double2(digit_f64<BGBIT>(tl, grp), -digit_f64<BGBIT>(th, grp));              // tgsw.jl:104-116
         }
+        lap(0);
         fft512_forward(a, w, X1, X2, t, bar_id);
+        lap(1);
         {
             const uint32_t dst = r_land + (uint32_t)(((buf * 2 + grp) * kSpectrum + t) * 16);
 #pragma unroll
@@ -110,36 +130,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) blind_rotate
         }
 #pragma unroll
         for (int e = 0; e < 8; e++) X1[e * 64 + t] = a[e];   // X1 is free: every thread of the group passed the 2nd barrier
+        lap(2);
         __syncthreads();   // A: the sibling group's spectrum is published, all reads of acc done
+        lap(3);
+        // the next iteration's key goes into the other set of slots NOW: the fill (64 KB through the shared-memory pipe)
+        // then coincides with the window in which the warps sit behind their remote stores anyway, not with a transform
+        // (issued after barrier B it made the inverse transform 700 cycles longer)
+        if (t < 32 && i + 1 < A.n_iter) issue_keys(i + 1);
         double2 o[8];
 #pragma unroll
         for (int e = 0; e < 8; e++) o[e] = make_double2(0.0, 0.0);
+        mbar_wait(kbar + buf * 2 + grp, (uint32_t)(i >> 1) & 1u);   // the four key spectra of this iteration (issued an iteration ago)
         {   // own spectrum from registers
-            mbar_wait(kbar + grp * kClKeySlots + q_own, (uint32_t)i & 1u);
-            const double2* K = keys + ((size_t)grp * kClKeySlots + q_own) * kSpectrum + t;
+            const double2* K = keys + ((size_t)(buf * 2 + grp) * kClKeySlots + q_own) * kSpectrum + t;
 #pragma unroll
             for (int e = 0; e < 8; e++) cmac(o[e], a[e], K[e * 64]);                                  // tgsw.jl:128
         }
         {   // the sibling group's
-            mbar_wait(kbar + grp * kClKeySlots + q_sib, (uint32_t)i & 1u);
             const double2* F = xbuf + (size_t)(grp ^ 1) * (kSpectrum + kX2Elems) + t;
-            const double2* K = keys + ((size_t)grp * kClKeySlots + q_sib) * kSpectrum + t;
+            const double2* K = keys + ((size_t)(buf * 2 + grp) * kClKeySlots + q_sib) * kSpectrum + t;
 #pragma unroll
             for (int e = 0; e < 8; e++) cmac(o[e], F[e * 64], K[e * 64]);
         }
+        lap(4);
         mbar_wait(lbar + buf, (uint32_t)(i >> 1) & 1u);   // the peer's spectra have landed
+        lap(5);
 #pragma unroll
         for (int r = 0; r < L; r++) {
             const int q = peer * L + r;
-            mbar_wait(kbar + grp * kClKeySlots + q, (uint32_t)i & 1u);
             const double2* F = land + (size_t)(buf * 2 + r) * kSpectrum + t;
-            const double2* K = keys + ((size_t)grp * kClKeySlots + q) * kSpectrum + t;
+            const double2* K = keys + ((size_t)(buf * 2 + grp) * kClKeySlots + q) * kSpectrum + t;
 #pragma unroll
             for (int e = 0; e < 8; e++) cmac(o[e], F[e * 64], K[e * 64]);
         }
+        lap(6);
         __syncthreads();   // B: published spectra and key slots consumed
-        if (t == 0 && i + 1 < A.n_iter) issue_keys(i + 1);   // lands during the inverse + next forward transform
+        lap(7);
         fft512_inverse(o, w, X1, X2, t, bar_id);
+        lap(8);
 #pragma unroll
         for (int m = 0; m < 8; m++) {
             uint32_t vl = round_to_u32_fast<true>(o[m].x), vh = round_to_u32_fast<true>(-o[m].y);   // polynomials.jl:115-116
@@ -149,12 +177,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) blind_rotate
             atomicAdd(reinterpret_cast<unsigned int*>(p + j + 512), vh);
         }
         __syncthreads();   // C: accumulator updated
+        lap(9);
     }
+    if (PROBE && A.probe && blockIdx.x < 2 && (threadIdx.x & 31) == 0)
+        for (int k = 0; k < 10; k++) A.probe[(blockIdx.x * 4 + (threadIdx.x >> 5)) * 10 + k] = (unsigned long long)pr[k];
 
     // tlwe_extract_sample (tlwe.jl:55-59): a = (p_0, -p_{N-1}, ..., -p_1) from component 0, b = acc_b[0] from component 1
     int32_t* out = A.out + g * (kN + 1);
     if (c == 0) {
-        for (int x = threadIdx.x; x < kN; x += blockDim.x) out[x] = x == 0 ? p[0] : (int32_t)(0u - (uint32_t)p[kN - x]);
+        for (int x = threadIdx.x; x < kN; x += 128) out[x] = x == 0 ? p[0] : (int32_t)(0u - (uint32_t)p[kN - x]);
     } else if (threadIdx.x == 0) out[kN] = p[0];
     cluster_sync_all();   // neither CTA leaves while the other could still address its shared memory
 }

@@ -44,7 +44,7 @@ struct tfhe_b200_ctx {
     int G = 0;                       // gates per CTA of the blind-rotation kernel (0 = default, see launch_br_np)
     int sm_count = 148;
     int l2_hint = 0;                 // TFHE_B200_L2HINT=1: key chunks fetched with the L2 evict_last policy (K3 with the producer warpgroup)
-    int cluster = 0;                 // TFHE_B200_CLUSTER=1: batches of <= 1 gate per two SMs take the two-CTA cluster kernel
+    int cluster = 1;                 // batches of <= 1 gate per two SMs (two-piece 80-bit set) take the two-CTA cluster kernel; TFHE_B200_CLUSTER=0: off, 2: phase probe
     int lowlat = 1;                  // batches of <= 1 gate per SM: one gate per CTA spread over 4 groups + sliced key switch
     int ks_tile = 1;                 // large batches: tiled key switch (TFHE_B200_KS_TILE=0: one CTA per ciphertext)
     int mk_ring = 1;                 // MK blind rotation: 1 = TMA key ring, several gates per CTA (mk_blind_rotate.cuh)
@@ -171,11 +171,32 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
                     // 592 gates 6.45 ms on the 4-gates-per-CTA kernel, so up to 3 waves the latency kernel also wins
                     if constexpr (L == 2 && NP == 2) {
                         // at most one gate per two SMs: a cluster of two CTAs per gate (blind_rotate_cluster.cuh)
+                        if (2 * A.count <= sms && ctx->lowlat && ctx->cluster == 2) {   // clock64 phase probe (development)
+                            BlindRotateArgs B = A;
+                            CU(cudaMalloc(&B.probe, 80 * sizeof(unsigned long long)));
+                            auto kern = blind_rotate_cluster_kernel<BGBIT, 1>;
+                            const size_t smem = br_cluster_smem_bytes(A.n_pad);
+                            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                            kern<<<(unsigned)(2 * A.count), kClThreads, smem, s>>>(B);
+                            CU(cudaGetLastError());
+                            ctx->launches++;
+                            std::vector<unsigned long long> h(80);
+                            CU(cudaStreamSynchronize(s));
+                            CU(cudaMemcpy(h.data(), B.probe, h.size() * 8, cudaMemcpyDeviceToHost));
+                            CU(cudaFree(B.probe));
+                            static const char* names[10] = {"rotate", "fwd", "send", "barA", "own", "land", "peer", "barB", "inv", "upd+barC"};
+                            for (int w = 0; w < 8; w++) {
+                                fprintf(stderr, "cluster probe cta %d warp %d (cycles per iteration):", w / 4, w % 4);
+                                for (int k = 0; k < 10; k++) fprintf(stderr, " %s %.0f", names[k], (double)h[w * 10 + k] / A.n_iter);
+                                fprintf(stderr, "\n");
+                            }
+                            return 0;
+                        }
                         if (2 * A.count <= sms && ctx->lowlat && ctx->cluster) {
                             auto kern = blind_rotate_cluster_kernel<BGBIT>;
                             const size_t smem = br_cluster_smem_bytes(A.n_pad);
                             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                            kern<<<(unsigned)(2 * A.count), 128, smem, s>>>(A);
+                            kern<<<(unsigned)(2 * A.count), kClThreads, smem, s>>>(A);
                             CU(cudaGetLastError());
                             ctx->launches++;
                             return 0;
@@ -399,7 +420,7 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
     c->mk_pw = env_int("TFHE_B200_MK_PW", 1);
     c->lowlat = env_int("TFHE_B200_LOWLAT", 1);
     c->l2_hint = env_int("TFHE_B200_L2HINT", 0);
-    c->cluster = env_int("TFHE_B200_CLUSTER", 0);
+    c->cluster = env_int("TFHE_B200_CLUSTER", 1);
     c->ks_tile = env_int("TFHE_B200_KS_TILE", 1);
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) c->sm_count = prop.multiProcessorCount; }
     {   // gates per host-staged chunk: at least one wave of CTAs, never zero or negative
