@@ -80,6 +80,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k_swap(int m
             if (threadIdx.x == 0) mbar_expect(mbar + buf, 2 * kSpec * 16);
             if (t == 0) bulk_s2s(r_land + (buf * 2 + grp) * kSpec * 16, smem_u32(src + grp * kSpec), kSpec * 16, r_bar + buf * 8);
             mbar_wait(mbar + buf, par);
+        } else if (mode == 5) {   // group 0 by st.async, group 1 by one bulk copy: do the two paths add up?
+            if (threadIdx.x == 0) mbar_expect(mbar + buf, 2 * kSpec * 16);
+            if (grp == 0) {
+#pragma unroll
+                for (int e = 0; e < 8; e++)
+                    st_async16(r_land + ((buf * 2 + grp) * kSpec + e * 64 + t) * 16, src[grp * kSpec + e * 64 + t], r_bar + buf * 8);
+            } else if (t == 0) bulk_s2s(r_land + (buf * 2 + grp) * kSpec * 16, smem_u32(src + grp * kSpec), kSpec * 16, r_bar + buf * 8);
+            mbar_wait(mbar + buf, par);
+        } else if (mode == 6) {   // half the volume (one spectrum each way) by st.async: is the cost linear in bytes?
+            if (threadIdx.x == 0) mbar_expect(mbar + buf, kSpec * 16);
+            if (grp == 0) {
+#pragma unroll
+                for (int e = 0; e < 8; e++)
+                    st_async16(r_land + ((buf * 2 + grp) * kSpec + e * 64 + t) * 16, src[grp * kSpec + e * 64 + t], r_bar + buf * 8);
+            }
+            mbar_wait(mbar + buf, par);
         } else if (mode == 2) {
 #pragma unroll
             for (int e = 0; e < 8; e++)
@@ -98,7 +114,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) k_swap(int m
                 }
         }
         // consume: read what landed (the real kernel multiplies it with the key)
-        if (mode <= 2) {
+        if (mode <= 2 || mode == 5) {
 #pragma unroll
             for (int e = 0; e < 8; e++)
 #pragma unroll
@@ -122,11 +138,12 @@ int main() {
     cudaMalloc(&d_chk, max_ctas * 128 * sizeof(double));
     const size_t smem = (2 + 4) * kSpec * 16 + 64;
     cudaFuncSetAttribute(k_swap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const char* names[] = {"st.async 16 B", "cp.async.bulk 8 KB", "st.shared::cluster + barrier.cluster", "barrier.cluster only", "barrier.cluster + ld.shared::cluster"};
+    const char* names[] = {"st.async 16 B", "cp.async.bulk 8 KB", "st.shared::cluster + barrier.cluster", "barrier.cluster only", "barrier.cluster + ld.shared::cluster",
+                           "half st.async + half cp.async.bulk", "st.async, 8 KB each way (no consume)"};
     printf("{\"iters\": %d, \"bytes_each_way\": %d, \"results\": [\n", iters, 2 * kSpec * 16);
     bool first = true;
     for (int ctas : {2, 148}) {
-        for (int mode = 0; mode < 5; mode++) {
+        for (int mode = 0; mode < 7; mode++) {
             k_swap<<<ctas, 128, smem>>>(mode, iters, d_cyc, d_chk);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { fprintf(stderr, "mode %d: %s\n", mode, cudaGetErrorString(e)); return 1; }
@@ -137,7 +154,7 @@ int main() {
             long long mx = 0; for (auto c : cyc) mx = c > mx ? c : mx;
             // expected sum per thread per iteration for modes 0-2, 4: sum over q,e of (peer*10000 + idx) - idx = 16 * peer * 10000
             bool ok = true;
-            if (mode != 3)
+            if (mode != 3 && mode != 6)
                 for (int b = 0; b < ctas; b++)
                     for (int th = 0; th < 128; th++)
                         if (chk[b * 128 + th] != 16.0 * ((b & 1) ^ 1) * 10000.0 * iters) ok = false;
