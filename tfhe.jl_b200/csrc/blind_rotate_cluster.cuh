@@ -1,4 +1,5 @@
-// blind_rotate_cluster.cuh — K3C: blind rotation of ONE gate by a CLUSTER of two CTAs (two SMs), 80-bit set, two pieces.
+// blind_rotate_cluster.cuh — K3C: blind rotation of ONE gate by a CLUSTER of two CTAs (two SMs), two-piece transform
+// (described for l = 2; l = 3 has three groups per CTA and six key spectra per output).
 //
 // K3L (blind_rotate_lowlat.cuh) runs the four forward and four inverse transforms of an iteration at once on one SM; both
 // phases are bound by that SM's FP64 rate (clock64 probe).  Here CTA c of the pair owns accumulator
@@ -45,63 +46,67 @@ __device__ __forceinline__ void st_async16(uint32_t remote_addr, double2 v, uint
                  ::"r"(remote_addr), "l"(__double_as_longlong(v.x)), "l"(__double_as_longlong(v.y)), "r"(remote_bar) : "memory");
 }
 
-constexpr int kClThreads = 128;  // two 64-thread groups
-constexpr int kClKeySlots = 4;   // all four key spectra of an output are prefetched during the previous iteration
-__host__ __device__ constexpr size_t br_cluster_smem_bytes(int n_pad) {
-    return (size_t)2 * 2 * kClKeySlots * kSpectrum * 16   // key slots [buffer][output group][q], used alternately
-           + (size_t)2 * 2 * kSpectrum * 16           // landing buffers [2][r]
-           + 128                                      // mbarriers: 2 x 2 key + 2 landing
-           + (size_t)2 * (kSpectrum + kX2Elems) * 16  // X1, X2 per group
+// l = 2: all four key spectra of an output fit twice (two sets of slots, filled alternately); l = 3 (128-bit set): six
+// spectra per output, one set (96 KB) beside 48 KB of landing buffers, refilled after barrier B
+template <int L> __host__ __device__ constexpr int br_cluster_key_sets() { return L == 2 ? 2 : 1; }
+template <int L> __host__ __device__ constexpr size_t br_cluster_smem_bytes(int n_pad) {
+    return (size_t)br_cluster_key_sets<L>() * 2 * (2 * L) * kSpectrum * 16   // key slots [set][output group][q]
+           + (size_t)2 * L * kSpectrum * 16           // landing buffers [2][r]
+           + 128                                      // mbarriers: sets x 2 key + 2 landing
+           + (size_t)L * (kSpectrum + kX2Elems) * 16  // X1, X2 per group
            + 2 * kN * 4 + (size_t)n_pad * 4;          // accumulator (both components initialised, one maintained), mask
 }
 
-template <int BGBIT, int PROBE = 0>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kClThreads, 1) blind_rotate_cluster_kernel(BlindRotateArgs A) {
-    constexpr int L = 2, NP = 2, NQ = 4;
+// L groups of 64 threads per CTA: group r transforms digit r; groups 0 and 1 also own the outputs (c, low piece) and
+// (c, high piece).
+template <int L, int BGBIT, int PROBE = 0>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 * L, 1) blind_rotate_cluster_kernel(BlindRotateArgs A) {
+    constexpr int NP = 2, NQ = 2 * L, KSETS = br_cluster_key_sets<L>();
     constexpr uint32_t offset = decomp_offset<L, BGBIT>();
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double2* keys = reinterpret_cast<double2*>(smem_raw);                       // [buf][grp][q][512]
-    double2* land = keys + (size_t)2 * 2 * kClKeySlots * kSpectrum;             // [buf][r][512]
-    uint64_t* kbar = reinterpret_cast<uint64_t*>(land + (size_t)4 * kSpectrum); // [buf][grp]
-    uint64_t* lbar = kbar + 4;                                                  // [buf]
+    double2* keys = reinterpret_cast<double2*>(smem_raw);                         // [set][output group][q][512]
+    double2* land = keys + (size_t)KSETS * 2 * NQ * kSpectrum;                    // [buf][r][512]
+    uint64_t* kbar = reinterpret_cast<uint64_t*>(land + (size_t)2 * L * kSpectrum);   // [set][output group]
+    uint64_t* lbar = kbar + 2 * KSETS;                                            // [buf]
     double2* xbuf = reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(kbar) + 128);
-    int32_t* acc = reinterpret_cast<int32_t*>(xbuf + (size_t)2 * (kSpectrum + kX2Elems));
+    int32_t* acc = reinterpret_cast<int32_t*>(xbuf + (size_t)L * (kSpectrum + kX2Elems));
     int32_t* bara = acc + 2 * kN;
 
     const int t = threadIdx.x & 63, grp = threadIdx.x >> 6;
     const int bar_id = grp + 1;
     const int c = (int)cluster_ctarank();      // accumulator component of this CTA = output component c'
     const int peer = c ^ 1;
+    const bool outg = grp < NP;                // this group also owns output (c, piece grp)
     double2* X1 = xbuf + (size_t)grp * (kSpectrum + kX2Elems);
     double2* X2 = X1 + kSpectrum;
     const unsigned long long g = blockIdx.x >> 1;
-    TwiddlesFull w; w.load(A.E, t);
+    // 128 threads leave room for the full twiddle set; 192 threads (168 registers) keep the compact one
+    typename std::conditional<L == 2, TwiddlesFull, Twiddles>::type w; w.load(A.E, t);
 
     // output group pc = grp reads, for q = (cq, r), the spectrum BK[i][r][cq][c][pc]
-    // One barrier per (slot set, group) counts all four copies of an iteration; lanes 0..3 of the group's first warp issue
-    // one copy each in the same instructions.  (Measured alternatives: both warps of the group issuing two copies each,
-    // and a fifth warp that only issues — 1.146 and 1.122 ms against 1.111 ms: a warp that issues a bulk copy loses
-    // ~350 cycles whatever the number of copies, and the extra warp slows the transforms of its sub-partition.)
-    auto issue_keys = [&](int i) {   // called by the first warp of the group
-        const int kb = i & 1;
-        if (t == 0) mbar_arrive_expect_tx(kbar + kb * 2 + grp, (uint32_t)(NQ * kSpectrum * 16));
+    // One barrier per (slot set, group) counts all copies of an iteration; lanes 0..NQ-1 of the group's first warp issue
+    // one copy each in the same instructions.  (Measured alternatives: both warps of the group issuing half of the copies
+    // each, and an extra warp that only issues — 1.146 and 1.122 ms against 1.111 ms: a warp that issues a bulk copy
+    // loses ~350 cycles whatever the number of copies, and the extra warp slows the transforms of its sub-partition.)
+    auto issue_keys = [&](int i) {   // called by the first warp of an output group
+        const int ks = KSETS == 2 ? (i & 1) : 0;
+        if (t == 0) mbar_arrive_expect_tx(kbar + ks * 2 + grp, (uint32_t)(NQ * kSpectrum * 16));
         __syncwarp();
         if (t < NQ) {
             const int q = t, cq = q / L, r = q % L;
             const double2* src = A.bk_fft + ((((size_t)i * L + r) * 2 + cq) * 2 * NP + (size_t)c * NP + grp) * kSpectrum;
-            bulk_copy_g2s(keys + ((size_t)(kb * 2 + grp) * kClKeySlots + q) * kSpectrum, src, kSpectrum * 16, kbar + kb * 2 + grp);
+            bulk_copy_g2s(keys + ((size_t)(ks * 2 + grp) * NQ + q) * kSpectrum, src, kSpectrum * 16, kbar + ks * 2 + grp);
         }
     };
-    if (threadIdx.x < 6) mbar_init(kbar + threadIdx.x, 1);   // 4 key + 2 landing barriers, contiguous
+    if (threadIdx.x < 2 * KSETS + 2) mbar_init(kbar + threadIdx.x, 1);   // key + landing barriers, contiguous
     if (threadIdx.x == 0) mbar_fence_init();
     __syncthreads();
-    if (t < 32) issue_keys(0);
+    if (outg && t < 32) issue_keys(0);
     lowlat_prologue(A, g, acc, bara);
     cluster_sync_all();   // both CTAs' barriers are initialised before the first remote store can arrive (also a CTA barrier)
 
     const uint32_t r_land = cluster_map(smem_u32(land), (uint32_t)peer), r_lbar = cluster_map(smem_u32(lbar), (uint32_t)peer);
     int32_t* p = acc + c * kN;
-    const int q_own = c * L + grp, q_sib = c * L + (grp ^ 1);
     // PROBE: cycles per phase (rotate, forward, send + publish, barrier A, own products, landing wait, peer products,
     // barrier B, inverse, update + barrier C)
     long long pr[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, ck = 0;
@@ -110,8 +115,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kClThreads, 1) blind
     for (int i = 0; i < A.n_iter; i++) {   // bootstrap.jl:19-23; a zero rotation is executed (exact no-op)
         const int s = bara[i] & 2047;
         const int buf = i & 1;
+        const int ks = KSETS == 2 ? buf : 0;
+        const uint32_t kpar = (uint32_t)(KSETS == 2 ? (i >> 1) : i) & 1u;
         if (PROBE) ck = clock64();
-        if (threadIdx.x == 0) mbar_arrive_expect_tx(lbar + buf, (uint32_t)(2 * kSpectrum * 16));   // the peer's two spectra
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(lbar + buf, (uint32_t)(L * kSpectrum * 16));   // the peer's spectra
         double2 a[8];
 #pragma unroll
         for (int m = 0; m < 8; m++) {
@@ -124,68 +131,76 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kClThreads, 1) blind
         fft512_forward(a, w, X1, X2, t, bar_id);
         lap(1);
         {
-            const uint32_t dst = r_land + (uint32_t)(((buf * 2 + grp) * kSpectrum + t) * 16);
+            const uint32_t dst = r_land + (uint32_t)(((buf * L + grp) * kSpectrum + t) * 16);
 #pragma unroll
             for (int e = 0; e < 8; e++) st_async16(dst + (uint32_t)(e * 64 * 16), a[e], r_lbar + (uint32_t)(buf * 8));
         }
 #pragma unroll
         for (int e = 0; e < 8; e++) X1[e * 64 + t] = a[e];   // X1 is free: every thread of the group passed the 2nd barrier
         lap(2);
-        __syncthreads();   // A: the sibling group's spectrum is published, all reads of acc done
+        __syncthreads();   // A: the sibling groups' spectra are published, all reads of acc done
         lap(3);
-        // the next iteration's key goes into the other set of slots NOW: the fill (64 KB through the shared-memory pipe)
-        // then coincides with the window in which the warps sit behind their remote stores anyway, not with a transform
-        // (issued after barrier B it made the inverse transform 700 cycles longer)
-        if (t < 32 && i + 1 < A.n_iter) issue_keys(i + 1);
+        // two sets of slots: the next iteration's key goes into the other set NOW — the fill (64 KB through the
+        // shared-memory pipe) then coincides with the window in which the warps sit behind their remote stores anyway,
+        // not with a transform (issued after barrier B it made the inverse transform 700 cycles longer)
+        if (KSETS == 2 && outg && t < 32 && i + 1 < A.n_iter) issue_keys(i + 1);
         double2 o[8];
+        if (outg) {
 #pragma unroll
-        for (int e = 0; e < 8; e++) o[e] = make_double2(0.0, 0.0);
-        mbar_wait(kbar + buf * 2 + grp, (uint32_t)(i >> 1) & 1u);   // the four key spectra of this iteration (issued an iteration ago)
-        {   // own spectrum from registers
-            const double2* K = keys + ((size_t)(buf * 2 + grp) * kClKeySlots + q_own) * kSpectrum + t;
+            for (int e = 0; e < 8; e++) o[e] = make_double2(0.0, 0.0);
+            mbar_wait(kbar + ks * 2 + grp, kpar);   // the key spectra of this iteration (issued an iteration ago)
+            {   // this group's own spectrum straight from registers ...
+                const double2* K = keys + ((size_t)(ks * 2 + grp) * NQ + c * L + grp) * kSpectrum + t;
 #pragma unroll
-            for (int e = 0; e < 8; e++) cmac(o[e], a[e], K[e * 64]);                                  // tgsw.jl:128
-        }
-        {   // the sibling group's
-            const double2* F = xbuf + (size_t)(grp ^ 1) * (kSpectrum + kX2Elems) + t;
-            const double2* K = keys + ((size_t)(buf * 2 + grp) * kClKeySlots + q_sib) * kSpectrum + t;
+                for (int e = 0; e < 8; e++) cmac(o[e], a[e], K[e * 64]);                              // tgsw.jl:128
+            }
 #pragma unroll
-            for (int e = 0; e < 8; e++) cmac(o[e], F[e * 64], K[e * 64]);
+            for (int d = 1; d < L; d++) {   // ... then the sibling groups', while the peer's are in flight
+                const int r = grp + d < L ? grp + d : grp + d - L;
+                const double2* F = xbuf + (size_t)r * (kSpectrum + kX2Elems) + t;
+                const double2* K = keys + ((size_t)(ks * 2 + grp) * NQ + c * L + r) * kSpectrum + t;
+#pragma unroll
+                for (int e = 0; e < 8; e++) cmac(o[e], F[e * 64], K[e * 64]);
+            }
         }
         lap(4);
-        mbar_wait(lbar + buf, (uint32_t)(i >> 1) & 1u);   // the peer's spectra have landed
+        if (outg) mbar_wait(lbar + buf, (uint32_t)(i >> 1) & 1u);   // the peer's spectra have landed
         lap(5);
+        if (outg) {
 #pragma unroll
-        for (int r = 0; r < L; r++) {
-            const int q = peer * L + r;
-            const double2* F = land + (size_t)(buf * 2 + r) * kSpectrum + t;
-            const double2* K = keys + ((size_t)(buf * 2 + grp) * kClKeySlots + q) * kSpectrum + t;
+            for (int r = 0; r < L; r++) {
+                const double2* F = land + (size_t)(buf * L + r) * kSpectrum + t;
+                const double2* K = keys + ((size_t)(ks * 2 + grp) * NQ + peer * L + r) * kSpectrum + t;
 #pragma unroll
-            for (int e = 0; e < 8; e++) cmac(o[e], F[e * 64], K[e * 64]);
+                for (int e = 0; e < 8; e++) cmac(o[e], F[e * 64], K[e * 64]);
+            }
         }
         lap(6);
         __syncthreads();   // B: published spectra and key slots consumed
         lap(7);
-        fft512_inverse(o, w, X1, X2, t, bar_id);
-        lap(8);
+        if (outg) {
+            if (KSETS == 1 && t < 32 && i + 1 < A.n_iter) issue_keys(i + 1);   // one set: lands during the inverse + next forward transform
+            fft512_inverse(o, w, X1, X2, t, bar_id);
+            lap(8);
 #pragma unroll
-        for (int m = 0; m < 8; m++) {
-            uint32_t vl = round_to_u32_fast<true>(o[m].x), vh = round_to_u32_fast<true>(-o[m].y);   // polynomials.jl:115-116
-            if (grp == 1) { vl <<= 16; vh <<= 16; }
-            const int j = t + 64 * m;
-            atomicAdd(reinterpret_cast<unsigned int*>(p + j), vl);                                   // bootstrap.jl:22
-            atomicAdd(reinterpret_cast<unsigned int*>(p + j + 512), vh);
+            for (int m = 0; m < 8; m++) {
+                uint32_t vl = round_to_u32_fast<true>(o[m].x), vh = round_to_u32_fast<true>(-o[m].y);   // polynomials.jl:115-116
+                if (grp == 1) { vl <<= 16; vh <<= 16; }
+                const int j = t + 64 * m;
+                atomicAdd(reinterpret_cast<unsigned int*>(p + j), vl);                                   // bootstrap.jl:22
+                atomicAdd(reinterpret_cast<unsigned int*>(p + j + 512), vh);
+            }
         }
         __syncthreads();   // C: accumulator updated
         lap(9);
     }
-    if (PROBE && A.probe && blockIdx.x < 2 && (threadIdx.x & 31) == 0)
+    if (PROBE && A.probe && blockIdx.x < 2 && (threadIdx.x & 31) == 0 && grp < 2)
         for (int k = 0; k < 10; k++) A.probe[(blockIdx.x * 4 + (threadIdx.x >> 5)) * 10 + k] = (unsigned long long)pr[k];
 
     // tlwe_extract_sample (tlwe.jl:55-59): a = (p_0, -p_{N-1}, ..., -p_1) from component 0, b = acc_b[0] from component 1
     int32_t* out = A.out + g * (kN + 1);
     if (c == 0) {
-        for (int x = threadIdx.x; x < kN; x += 128) out[x] = x == 0 ? p[0] : (int32_t)(0u - (uint32_t)p[kN - x]);
+        for (int x = threadIdx.x; x < kN; x += 64 * L) out[x] = x == 0 ? p[0] : (int32_t)(0u - (uint32_t)p[kN - x]);
     } else if (threadIdx.x == 0) out[kN] = p[0];
     cluster_sync_all();   // neither CTA leaves while the other could still address its shared memory
 }

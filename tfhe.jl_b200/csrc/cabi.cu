@@ -169,15 +169,15 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
                     const unsigned long long sms = (unsigned long long)ctx->sm_count;
                     // measured (tools/latency_probe.py): one wave of 148 gates takes 1.95 ms on the latency kernel,
                     // 592 gates 6.45 ms on the 4-gates-per-CTA kernel, so up to 3 waves the latency kernel also wins
-                    if constexpr (L == 2 && NP == 2) {
+                    if constexpr (NP == 2) {
                         // at most one gate per two SMs: a cluster of two CTAs per gate (blind_rotate_cluster.cuh)
                         if (2 * A.count <= sms && ctx->lowlat && ctx->cluster == 2) {   // clock64 phase probe (development)
                             BlindRotateArgs B = A;
                             CU(cudaMalloc(&B.probe, 80 * sizeof(unsigned long long)));
-                            auto kern = blind_rotate_cluster_kernel<BGBIT, 1>;
-                            const size_t smem = br_cluster_smem_bytes(A.n_pad);
+                            auto kern = blind_rotate_cluster_kernel<L, BGBIT, 1>;
+                            const size_t smem = br_cluster_smem_bytes<L>(A.n_pad);
                             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                            kern<<<(unsigned)(2 * A.count), kClThreads, smem, s>>>(B);
+                            kern<<<(unsigned)(2 * A.count), 64 * L, smem, s>>>(B);
                             CU(cudaGetLastError());
                             ctx->launches++;
                             std::vector<unsigned long long> h(80);
@@ -192,11 +192,11 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
                             }
                             return 0;
                         }
-                        if (2 * A.count <= sms && ctx->lowlat && ctx->cluster) {
-                            auto kern = blind_rotate_cluster_kernel<BGBIT>;
-                            const size_t smem = br_cluster_smem_bytes(A.n_pad);
+                        if (2 * A.count <= sms && ctx->lowlat && ctx->cluster && br_cluster_smem_bytes<L>(A.n_pad) <= 227 * 1024) {
+                            auto kern = blind_rotate_cluster_kernel<L, BGBIT>;
+                            const size_t smem = br_cluster_smem_bytes<L>(A.n_pad);
                             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                            kern<<<(unsigned)(2 * A.count), kClThreads, smem, s>>>(A);
+                            kern<<<(unsigned)(2 * A.count), 64 * L, smem, s>>>(A);
                             CU(cudaGetLastError());
                             ctx->launches++;
                             return 0;
