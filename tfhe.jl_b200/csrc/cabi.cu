@@ -250,7 +250,9 @@ int launch_extern(tfhe_b200_ctx* ctx, const int32_t* acc, const int32_t* idx, in
 
 // latency path: several CTAs per ciphertext; the output rows must have been zero-initialised by the caller
 int launch_keyswitch_sliced(tfhe_b200_ctx* ctx, const KeyswitchArgs& A, size_t count, cudaStream_t s) {
-    const int slices = (int)std::min<size_t>(32, std::max<size_t>(1, (size_t)16 * ctx->sm_count / count));
+    // up to 256 CTAs per ciphertext (4 mask positions = 32 independent row loads each): a lone gate's key switch is a chain
+    // of L2/HBM round trips, one per position of a slice (1 gate: 70 us with 32 slices, measured under ncu)
+    const int slices = (int)std::min<size_t>(256, std::max<size_t>(1, (size_t)16 * ctx->sm_count / count));
     keyswitch_sliced_kernel<<<(unsigned)(count * slices), A.stride / 4, (size_t)(A.Nk / slices + 1) * sizeof(int32_t), s>>>(A, count, slices);
     CU(cudaGetLastError());
     ctx->launches++;
