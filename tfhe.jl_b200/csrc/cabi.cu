@@ -44,6 +44,7 @@ struct tfhe_b200_ctx {
     int G = 0;                       // gates per CTA of the blind-rotation kernel (0 = default, see launch_br_np)
     int sm_count = 148;
     int l2_hint = 0;                 // TFHE_B200_L2HINT=1: key chunks fetched with the L2 evict_last policy (K3 with the producer warpgroup)
+    int max_clusters = 0;            // two-CTA clusters of the latency kernel the device holds at once (cudaOccupancyMaxActiveClusters)
     int cluster = 1;                 // batches of <= 1 gate per two SMs (two-piece 80-bit set) take the two-CTA cluster kernel; TFHE_B200_CLUSTER=0: off, 2: phase probe
     int lowlat = 1;                  // batches of <= 1 gate per SM: one gate per CTA spread over 4 groups + sliced key switch
     int ks_tile = 1;                 // large batches: tiled key switch (TFHE_B200_KS_TILE=0: one CTA per ciphertext)
@@ -171,7 +172,7 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
                     // 592 gates 6.45 ms on the 4-gates-per-CTA kernel, so up to 3 waves the latency kernel also wins
                     if constexpr (NP == 2) {
                         // at most one gate per two SMs: a cluster of two CTAs per gate (blind_rotate_cluster.cuh)
-                        if (2 * A.count <= sms && ctx->lowlat && ctx->cluster == 2) {   // clock64 phase probe (development)
+                        if (A.count <= (unsigned long long)ctx->max_clusters && ctx->lowlat && ctx->cluster == 2) {   // clock64 phase probe (development)
                             BlindRotateArgs B = A;
                             CU(cudaMalloc(&B.probe, 80 * sizeof(unsigned long long)));
                             auto kern = blind_rotate_cluster_kernel<L, BGBIT, 1>;
@@ -192,7 +193,7 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
                             }
                             return 0;
                         }
-                        if (2 * A.count <= sms && ctx->lowlat && ctx->cluster && br_cluster_smem_bytes<L>(A.n_pad) <= 227 * 1024) {
+                        if (A.count <= (unsigned long long)ctx->max_clusters && ctx->lowlat && ctx->cluster && br_cluster_smem_bytes<L>(A.n_pad) <= 227 * 1024) {
                             auto kern = blind_rotate_cluster_kernel<L, BGBIT>;
                             const size_t smem = br_cluster_smem_bytes<L>(A.n_pad);
                             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -425,6 +426,25 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
     c->cluster = env_int("TFHE_B200_CLUSTER", 1);
     c->ks_tile = env_int("TFHE_B200_KS_TILE", 1);
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) c->sm_count = prop.multiProcessorCount; }
+    if (c->cluster && c->NP == 2 && P.parties <= 1) {
+        // how many two-CTA clusters of the latency kernel the device can hold at once (0 on a device or partition that
+        // cannot co-schedule CTA pairs with this much shared memory: the one-CTA latency kernel takes over)
+        auto probe = [&](auto kern, int threads, size_t smem) {
+            int n = 0;
+            cudaLaunchConfig_t cfg = {};
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.gridDim = dim3(2 * (unsigned)c->sm_count); cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = smem;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+                cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+            return n;
+        };
+        const int n_pad = (P.n + 31) & ~31;
+        if (P.l == 2 && P.bgbit == 10) c->max_clusters = probe(blind_rotate_cluster_kernel<2, 10>, 128, br_cluster_smem_bytes<2>(n_pad));
+        else if (P.l == 3 && P.bgbit == 7) c->max_clusters = probe(blind_rotate_cluster_kernel<3, 7>, 192, br_cluster_smem_bytes<3>(n_pad));
+    }
     {   // gates per host-staged chunk: at least one wave of CTAs, never zero or negative
         const long long v = env_int("TFHE_B200_CHUNK", 1 << 16);
         c->chunk = (size_t)std::max<long long>(v, (long long)4 * c->sm_count);
