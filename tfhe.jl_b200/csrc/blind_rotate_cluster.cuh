@@ -49,6 +49,9 @@ __device__ __forceinline__ void st_async16(uint32_t remote_addr, double2 v, uint
 // l = 2: all four key spectra of an output fit twice (two sets of slots, filled alternately); l = 3 (128-bit set): six
 // spectra per output, one set (96 KB) beside 48 KB of landing buffers, refilled after barrier B
 template <int L> __host__ __device__ constexpr int br_cluster_key_sets() { return L == 2 ? 2 : 1; }
+// l = 3: a seventh warp that only issues the key copies (1.83 -> 1.70 ms); l = 2: the first warp of each output group issues
+// them itself (with the extra warp: 1.074 instead of 1.062 ms — it slows the transforms of its sub-partition)
+template <int L> __host__ __device__ constexpr int br_cluster_threads() { return 64 * L + (L == 3 ? 32 : 0); }
 template <int L> __host__ __device__ constexpr size_t br_cluster_smem_bytes(int n_pad) {
     return (size_t)br_cluster_key_sets<L>() * 2 * (2 * L) * kSpectrum * 16   // key slots [set][output group][q]
            + (size_t)2 * L * kSpectrum * 16           // landing buffers [2][r]
@@ -60,14 +63,20 @@ template <int L> __host__ __device__ constexpr size_t br_cluster_smem_bytes(int 
 // L groups of 64 threads per CTA: group r transforms digit r; groups 0 and 1 also own the outputs (c, low piece) and
 // (c, high piece).
 template <int L, int BGBIT, int PROBE = 0>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 * L, 1) blind_rotate_cluster_kernel(BlindRotateArgs A) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(br_cluster_threads<L>(), 1) blind_rotate_cluster_kernel(BlindRotateArgs A) {
     constexpr int NP = 2, NQ = 2 * L, KSETS = br_cluster_key_sets<L>();
+    constexpr int NT = 64 * L, NTP = br_cluster_threads<L>();   // compute threads; + the warp that only issues the key copies (l = 3)
+    constexpr bool KW = NTP > NT;
+    // CTA barriers as named barriers: the key warp joins only the one after which it issues (A with two sets of slots, B with one)
+    auto bar_a = [&]() { if (KSETS == 2) asm volatile("bar.sync 8, %0;" ::"n"(NTP) : "memory"); else asm volatile("bar.sync 8, %0;" ::"n"(NT) : "memory"); };
+    auto bar_b = [&]() { if (KSETS == 1) asm volatile("bar.sync 9, %0;" ::"n"(NTP) : "memory"); else asm volatile("bar.sync 9, %0;" ::"n"(NT) : "memory"); };
+    auto bar_c = [&]() { asm volatile("bar.sync 10, %0;" ::"n"(NT) : "memory"); };
     constexpr uint32_t offset = decomp_offset<L, BGBIT>();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double2* keys = reinterpret_cast<double2*>(smem_raw);                         // [set][output group][q][512]
     double2* land = keys + (size_t)KSETS * 2 * NQ * kSpectrum;                    // [buf][r][512]
     uint64_t* kbar = reinterpret_cast<uint64_t*>(land + (size_t)2 * L * kSpectrum);   // [set][output group]
-    uint64_t* lbar = kbar + 2 * KSETS;                                            // [buf]
+    uint64_t* lbar = kbar + 2 * KSETS;                                            // [buf][r]: one per landing spectrum
     double2* xbuf = reinterpret_cast<double2*>(reinterpret_cast<unsigned char*>(kbar) + 128);
     int32_t* acc = reinterpret_cast<int32_t*>(xbuf + (size_t)L * (kSpectrum + kX2Elems));
     int32_t* bara = acc + 2 * kN;
@@ -83,28 +92,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 * L, 1) blind_rot
     // 128 threads leave room for the full twiddle set; 192 threads (168 registers) keep the compact one
     typename std::conditional<L == 2, TwiddlesFull, Twiddles>::type w; w.load(A.E, t);
 
-    // output group pc = grp reads, for q = (cq, r), the spectrum BK[i][r][cq][c][pc]
-    // One barrier per (slot set, group) counts all copies of an iteration; lanes 0..NQ-1 of the group's first warp issue
-    // one copy each in the same instructions.  (Measured alternatives: both warps of the group issuing half of the copies
-    // each, and an extra warp that only issues — 1.146 and 1.122 ms against 1.111 ms: a warp that issues a bulk copy
-    // loses ~350 cycles whatever the number of copies, and the extra warp slows the transforms of its sub-partition.)
-    auto issue_keys = [&](int i) {   // called by the first warp of an output group
+    // output group pc reads, for q = (cq, r), the spectrum BK[i][r][cq][c][pc].  One barrier per (slot set, group) counts all
+    // copies of an iteration; one lane per copy issues them in the same instructions (a warp that issues a bulk copy loses
+    // ~350-450 cycles whatever the number of copies).
+    auto issue_keys = [&](int i) {   // called by one whole warp: the key warp (all outputs) or the first warp of an output group (its own)
+        const int lane = threadIdx.x & 31, kg = KW ? lane / NQ : grp, q = lane % NQ;
         const int ks = KSETS == 2 ? (i & 1) : 0;
-        if (t == 0) mbar_arrive_expect_tx(kbar + ks * 2 + grp, (uint32_t)(NQ * kSpectrum * 16));
+        const bool mine = lane < (KW ? 2 * NQ : NQ);
+        if (mine && q == 0) mbar_arrive_expect_tx(kbar + ks * 2 + kg, (uint32_t)(NQ * kSpectrum * 16));
         __syncwarp();
-        if (t < NQ) {
-            const int q = t, cq = q / L, r = q % L;
-            const double2* src = A.bk_fft + ((((size_t)i * L + r) * 2 + cq) * 2 * NP + (size_t)c * NP + grp) * kSpectrum;
-            bulk_copy_g2s(keys + ((size_t)(ks * 2 + grp) * NQ + q) * kSpectrum, src, kSpectrum * 16, kbar + ks * 2 + grp);
+        if (mine) {
+            const int cq = q / L, r = q % L;
+            const double2* src = A.bk_fft + ((((size_t)i * L + r) * 2 + cq) * 2 * NP + (size_t)c * NP + kg) * kSpectrum;
+            bulk_copy_g2s(keys + ((size_t)(ks * 2 + kg) * NQ + q) * kSpectrum, src, kSpectrum * 16, kbar + ks * 2 + kg);
         }
     };
-    if (threadIdx.x < 2 * KSETS + 2) mbar_init(kbar + threadIdx.x, 1);   // key + landing barriers, contiguous
+    const bool issuer = KW ? threadIdx.x >= NT : (outg && t < 32);
+    if (threadIdx.x < 2 * KSETS + 2 * L) mbar_init(kbar + threadIdx.x, 1);   // key + landing barriers, contiguous
     if (threadIdx.x == 0) mbar_fence_init();
     __syncthreads();
-    if (outg && t < 32) issue_keys(0);
+    if (issuer) issue_keys(0);
     lowlat_prologue(A, g, acc, bara);
     cluster_sync_all();   // both CTAs' barriers are initialised before the first remote store can arrive (also a CTA barrier)
 
+    if (KW && threadIdx.x >= NT) {   // the key warp
+        for (int i = 0; i < A.n_iter; i++) {
+            if (KSETS == 2) bar_a(); else bar_b();
+            if (i + 1 < A.n_iter) issue_keys(i + 1);
+        }
+        cluster_sync_all();
+        return;
+    }
     const uint32_t r_land = cluster_map(smem_u32(land), (uint32_t)peer), r_lbar = cluster_map(smem_u32(lbar), (uint32_t)peer);
     int32_t* p = acc + c * kN;
     // PROBE: cycles per phase (rotate, forward, send + publish, barrier A, own products, landing wait, peer products,
@@ -118,7 +136,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 * L, 1) blind_rot
         const int ks = KSETS == 2 ? buf : 0;
         const uint32_t kpar = (uint32_t)(KSETS == 2 ? (i >> 1) : i) & 1u;
         if (PROBE) ck = clock64();
-        if (threadIdx.x == 0) mbar_arrive_expect_tx(lbar + buf, (uint32_t)(L * kSpectrum * 16));   // the peer's spectra
+        if (threadIdx.x < L) mbar_arrive_expect_tx(lbar + buf * L + threadIdx.x, (uint32_t)(kSpectrum * 16));   // the peer's spectra, one barrier each
         double2 a[8];
 #pragma unroll
         for (int m = 0; m < 8; m++) {
@@ -130,20 +148,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 * L, 1) blind_rot
         lap(0);
         fft512_forward(a, w, X1, X2, t, bar_id);
         lap(1);
-        {
+        // Group 1 sends AFTER barrier A and its first product: the fabric moves ~12 B/clk whatever the number of senders, so
+        // staggering the sends lets the peer's first spectrum land ~half a transfer earlier, and its product (one landing
+        // barrier per spectrum) runs while the second one is still in flight (1.09 -> 1.05 ms)
+        const bool late_send = L == 2 && grp == 1;
+        if (!late_send) {
             const uint32_t dst = r_land + (uint32_t)(((buf * L + grp) * kSpectrum + t) * 16);
 #pragma unroll
-            for (int e = 0; e < 8; e++) st_async16(dst + (uint32_t)(e * 64 * 16), a[e], r_lbar + (uint32_t)(buf * 8));
+            for (int e = 0; e < 8; e++) st_async16(dst + (uint32_t)(e * 64 * 16), a[e], r_lbar + (uint32_t)((buf * L + grp) * 8));
         }
 #pragma unroll
         for (int e = 0; e < 8; e++) X1[e * 64 + t] = a[e];   // X1 is free: every thread of the group passed the 2nd barrier
         lap(2);
-        __syncthreads();   // A: the sibling groups' spectra are published, all reads of acc done
+        // A: the sibling groups' spectra are published, all reads of acc done.  With two sets of slots the key warp now
+        // issues the next iteration's key into the other set — the fill (64 KB through the shared-memory pipe) then
+        // coincides with the window in which the warps sit behind their remote stores anyway, not with a transform
+        // (issued after barrier B it made the inverse transform 700 cycles longer)
+        bar_a();
         lap(3);
-        // two sets of slots: the next iteration's key goes into the other set NOW — the fill (64 KB through the
-        // shared-memory pipe) then coincides with the window in which the warps sit behind their remote stores anyway,
-        // not with a transform (issued after barrier B it made the inverse transform 700 cycles longer)
-        if (KSETS == 2 && outg && t < 32 && i + 1 < A.n_iter) issue_keys(i + 1);
+        if (!KW && KSETS == 2 && issuer && i + 1 < A.n_iter) issue_keys(i + 1);
         double2 o[8];
         if (outg) {
 #pragma unroll
@@ -153,6 +176,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 * L, 1) blind_rot
                 const double2* K = keys + ((size_t)(ks * 2 + grp) * NQ + c * L + grp) * kSpectrum + t;
 #pragma unroll
                 for (int e = 0; e < 8; e++) cmac(o[e], a[e], K[e * 64]);                              // tgsw.jl:128
+            }
+            if (late_send) {
+                const uint32_t dst = r_land + (uint32_t)(((buf * L + grp) * kSpectrum + t) * 16);
+#pragma unroll
+                for (int e = 0; e < 8; e++) st_async16(dst + (uint32_t)(e * 64 * 16), a[e], r_lbar + (uint32_t)((buf * L + grp) * 8));
             }
 #pragma unroll
             for (int d = 1; d < L; d++) {   // ... then the sibling groups', while the peer's are in flight
@@ -164,11 +192,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 * L, 1) blind_rot
             }
         }
         lap(4);
-        if (outg) mbar_wait(lbar + buf, (uint32_t)(i >> 1) & 1u);   // the peer's spectra have landed
         lap(5);
         if (outg) {
 #pragma unroll
             for (int r = 0; r < L; r++) {
+                mbar_wait(lbar + buf * L + r, (uint32_t)(i >> 1) & 1u);   // the peer's spectrum r has landed
                 const double2* F = land + (size_t)(buf * L + r) * kSpectrum + t;
                 const double2* K = keys + ((size_t)(ks * 2 + grp) * NQ + peer * L + r) * kSpectrum + t;
 #pragma unroll
@@ -176,10 +204,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 * L, 1) blind_rot
             }
         }
         lap(6);
-        __syncthreads();   // B: published spectra and key slots consumed
+        bar_b();   // B: published spectra and key slots consumed (one set of slots: refilled now)
         lap(7);
+        if (!KW && KSETS == 1 && issuer && i + 1 < A.n_iter) issue_keys(i + 1);
         if (outg) {
-            if (KSETS == 1 && t < 32 && i + 1 < A.n_iter) issue_keys(i + 1);   // one set: lands during the inverse + next forward transform
             fft512_inverse(o, w, X1, X2, t, bar_id);
             lap(8);
 #pragma unroll
@@ -191,7 +219,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 * L, 1) blind_rot
                 atomicAdd(reinterpret_cast<unsigned int*>(p + j + 512), vh);
             }
         }
-        __syncthreads();   // C: accumulator updated
+        bar_c();   // C: accumulator updated
         lap(9);
     }
     if (PROBE && A.probe && blockIdx.x < 2 && (threadIdx.x & 31) == 0 && grp < 2)
@@ -200,7 +228,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 * L, 1) blind_rot
     // tlwe_extract_sample (tlwe.jl:55-59): a = (p_0, -p_{N-1}, ..., -p_1) from component 0, b = acc_b[0] from component 1
     int32_t* out = A.out + g * (kN + 1);
     if (c == 0) {
-        for (int x = threadIdx.x; x < kN; x += 64 * L) out[x] = x == 0 ? p[0] : (int32_t)(0u - (uint32_t)p[kN - x]);
+        for (int x = threadIdx.x; x < kN; x += NT) out[x] = x == 0 ? p[0] : (int32_t)(0u - (uint32_t)p[kN - x]);
     } else if (threadIdx.x == 0) out[kN] = p[0];
     cluster_sync_all();   // neither CTA leaves while the other could still address its shared memory
 }

@@ -178,7 +178,7 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
                             auto kern = blind_rotate_cluster_kernel<L, BGBIT, 1>;
                             const size_t smem = br_cluster_smem_bytes<L>(A.n_pad);
                             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                            kern<<<(unsigned)(2 * A.count), 64 * L, smem, s>>>(B);
+                            kern<<<(unsigned)(2 * A.count), br_cluster_threads<L>(), smem, s>>>(B);
                             CU(cudaGetLastError());
                             ctx->launches++;
                             std::vector<unsigned long long> h(80);
@@ -197,7 +197,7 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
                             auto kern = blind_rotate_cluster_kernel<L, BGBIT>;
                             const size_t smem = br_cluster_smem_bytes<L>(A.n_pad);
                             CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                            kern<<<(unsigned)(2 * A.count), 64 * L, smem, s>>>(A);
+                            kern<<<(unsigned)(2 * A.count), br_cluster_threads<L>(), smem, s>>>(A);
                             CU(cudaGetLastError());
                             ctx->launches++;
                             return 0;
@@ -442,8 +442,8 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
             return n;
         };
         const int n_pad = (P.n + 31) & ~31;
-        if (P.l == 2 && P.bgbit == 10) c->max_clusters = probe(blind_rotate_cluster_kernel<2, 10>, 128, br_cluster_smem_bytes<2>(n_pad));
-        else if (P.l == 3 && P.bgbit == 7) c->max_clusters = probe(blind_rotate_cluster_kernel<3, 7>, 192, br_cluster_smem_bytes<3>(n_pad));
+        if (P.l == 2 && P.bgbit == 10) c->max_clusters = probe(blind_rotate_cluster_kernel<2, 10>, br_cluster_threads<2>(), br_cluster_smem_bytes<2>(n_pad));
+        else if (P.l == 3 && P.bgbit == 7) c->max_clusters = probe(blind_rotate_cluster_kernel<3, 7>, br_cluster_threads<3>(), br_cluster_smem_bytes<3>(n_pad));
     }
     {   // gates per host-staged chunk: at least one wave of CTAs, never zero or negative
         const long long v = env_int("TFHE_B200_CHUNK", 1 << 16);
