@@ -62,7 +62,7 @@ extern "C" {
 typedef struct {
     int32_t n;        /* lwe_size */
     int32_t N;        /* tlwe_polynomial_degree (must be 1024) */
-    int32_t k;        /* tlwe_mask_size (must be 1) */
+    int32_t k;        /* tlwe_mask_size (1; 2 and 3 on single-key contexts: blind_rotate_wide.cuh) */
     int32_t l;        /* bs_decomp_length */
     int32_t bgbit;    /* bs_log2_base */
     int32_t t;        /* ks_decomp_length */
@@ -168,7 +168,7 @@ int tfhe_b200_mk_extern_product_batch(tfhe_b200_ctx* ctx, const int32_t* acc, co
 /* Every function here that consumes randomness exists in two forms: *_words takes the random words from the caller
  * (so a CPU oracle fed the same words must produce the same bits), the other generates them on the device with a
  * counter-based generator (Philox4x32-10; mask words = stream 1 of `seed`, Gaussian noise = Box-Muller over stream 2)
- * and never moves them through the host.  key_len is n for single-key and p*n for MK ciphertexts.  k = 1 only. */
+ * and never moves them through the host.  key_len is n for single-key and p*n for MK ciphertexts. */
 /* word i of Philox stream (seed, stream), i < count (tests, reproducibility) */
 int tfhe_b200_random_words(tfhe_b200_ctx* ctx, uint64_t seed, uint64_t stream, int32_t* out, size_t count);
 /* lwe_encrypt (lwe.jl:38-55): out[g] = (a[g], mu[g] + noise[g] + <a[g], key>); a [count][key_len], out [count][key_len+1] */
@@ -185,8 +185,8 @@ int tfhe_b200_encrypt_batch_dev(tfhe_b200_ctx* ctx, const int32_t* key, int32_t 
 int tfhe_b200_lwe_phase_batch(tfhe_b200_ctx* ctx, const int32_t* key, int32_t key_len, const int32_t* ct, int32_t* phase,
                               uint8_t* bits_out, size_t count);
 /* BootstrapKey (bootstrap.jl:6-15; tgsw_encrypt tgsw.jl:84-88, tlwe_encrypt_zero tlwe.jl:63-73) generated, transformed
- * and loaded on the device: lwe_key [n], tlwe_key [N], a / noise [n*l*2][N] (sample (i, r, j): mask polynomial and
- * noise polynomial).  bk_out (nullable) receives the coefficient form [n][l][2][2][N]. */
+ * and loaded on the device: lwe_key [n], tlwe_key [k][N], a [n*l*(k+1)][k][N], noise [n*l*(k+1)][N] (sample (i, r, j):
+ * its k mask polynomials and its noise polynomial).  bk_out (nullable) receives the coefficient form [n][l][k+1][k+1][N]. */
 int tfhe_b200_keygen_bk_words(tfhe_b200_ctx* ctx, const int32_t* lwe_key, const int32_t* tlwe_key, const int32_t* a,
                               const int32_t* noise, int32_t* bk_out);
 int tfhe_b200_keygen_bk(tfhe_b200_ctx* ctx, const int32_t* lwe_key, const int32_t* tlwe_key, double sigma, uint64_t seed,

@@ -41,7 +41,7 @@ def test_no_cpu_fallback():
 def test_create_rejects_unsupported_parameters():
     lib = T.lib()
     h = ctypes.c_void_p()
-    for bad in (dict(N=2048), dict(k=2), dict(l=7, bgbit=3), dict(parties=3, l=2, bgbit=10)):
+    for bad in (dict(N=2048), dict(k=4), dict(k=0), dict(k=2, parties=2, l=4, bgbit=7), dict(l=7, bgbit=3), dict(parties=3, l=2, bgbit=10)):
         kw = dict(n=500, N=1024, k=1, l=2, bgbit=10, t=8, basebit=2, parties=1); kw.update(bad)
         rc = lib.tfhe_b200_create(ctypes.byref(_cabi.CParams(*[kw[f] for f in ("n", "N", "k", "l", "bgbit", "t", "basebit", "parties")])), 0, 0, ctypes.byref(h))
         assert rc == _cabi.EINVAL and not h.value

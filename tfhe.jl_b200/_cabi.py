@@ -316,12 +316,14 @@ class Context:
 
     def keygen_bk(self, lwe_key, tlwe_key, sigma=None, seed=None, a=None, noise=None, keep=True):
         """Generates, transforms and loads the bootstrapping key on the device; returns its int32 coefficient form
-        ([n][l][2][2][N]) when `keep`.  Either (sigma, seed) or explicit randomness (a, noise: [n*l*2][N])."""
+        ([n][l][k+1][k+1][N]) when `keep`.  Either (sigma, seed) or explicit randomness (a: [n*l*(k+1)][k][N] mask words,
+        noise: [n*l*(k+1)][N])."""
         lwe_key = _host(lwe_key, (self.n,)); tlwe_key = _host(tlwe_key).reshape(-1)
-        assert tlwe_key.size == self.N and self.k == 1
-        out = np.empty((self.n, self.l, 2, 2, self.N), dtype=np.int32) if keep else None
+        assert tlwe_key.size == self.N * self.k and self.parties == 1
+        k1 = self.k + 1
+        out = np.empty((self.n, self.l, k1, k1, self.N), dtype=np.int32) if keep else None
         if a is not None:
-            a = _host(a, (self.n * self.l * 2, self.N)); noise = _host(noise, (self.n * self.l * 2, self.N))
+            a = _host(np.reshape(a, (self.n * self.l * k1, self.k, self.N))); noise = _host(noise, (self.n * self.l * k1, self.N))
             self._ck(lib().tfhe_b200_keygen_bk_words(self._h, _addr(lwe_key), _addr(tlwe_key), _addr(a), _addr(noise), _addr(out)))
         else:
             self._ck(lib().tfhe_b200_keygen_bk(self._h, _addr(lwe_key), _addr(tlwe_key), float(sigma), int(seed), _addr(out)))

@@ -207,7 +207,7 @@ class CloudKey:                               # api.jl:111-127
         p = secret_key.params
         self.params = p
         self.mctx = None
-        if device_keygen and devices is None and p.tlwe_mask_size == 1:
+        if device_keygen and devices is None:
             self.ctx = _context(p, 1, device, flags)
             tlwe_key = rand_uniform_bool(rng, p.tlwe_mask_size, p.tlwe_polynomial_degree)
             seed = int(rng.integers(0, 2 ** 63))

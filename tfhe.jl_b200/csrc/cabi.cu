@@ -18,6 +18,7 @@
 #include "blind_rotate.cuh"
 #include "blind_rotate_lowlat.cuh"
 #include "blind_rotate_cluster.cuh"
+#include "blind_rotate_wide.cuh"
 #include "mk_kernels.cuh"
 #include "mk_blind_rotate.cuh"
 #include "mk_blind_rotate_lowlat.cuh"
@@ -224,10 +225,40 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
         return launch_br_g<L, BGBIT, NP, 4, 6, MODE>(ctx, A, s);   // a two-piece-only variant was asked for with one piece
     }
 }
+// mask size k > 1: two gates per CTA, output spectra in shared memory, key from L2
+template <int L, int BGBIT, int NP, int MODE>
+int launch_br_wide(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
+    const int kp1 = ctx->P.k + 1;
+    auto kern = blind_rotate_wide_kernel<L, BGBIT, NP, MODE>;
+    const size_t smem = br_wide_smem_bytes(NP, kp1, A.n_pad);
+    if (smem > 227 * 1024) return fail(ctx, TFHE_B200_EINVAL, "LWE dimension too large for the shared-memory layout");
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)((A.count + kWideGates - 1) / kWideGates), 64 * kWideGates, smem, s>>>(A, kp1);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+template <int L, int BGBIT, int NP>
+int launch_extern_wide(tfhe_b200_ctx* ctx, const int32_t* acc, const int32_t* idx, int32_t* out, size_t count, cudaStream_t s) {
+    const int kp1 = ctx->P.k + 1;
+    auto kern = extern_product_wide_kernel<L, BGBIT, NP>;
+    const size_t smem = br_wide_smem_bytes(NP, kp1, 0, 1);
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)count, 64, smem, s>>>(ctx->d_bk_fft, ctx->d_E, acc, idx, out, kp1);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
 template <int MODE>
 int launch_br(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
     const int l = ctx->P.l, bg = ctx->P.bgbit;
     if (A.count == 0) return 0;
+    if (ctx->P.k > 1) {   // tlwe_mask_size > 1 (api.jl:30,55): the k-generic kernel of blind_rotate_wide.cuh
+        if (l == 2 && bg == 10) return ctx->NP == 2 ? launch_br_wide<2, 10, 2, MODE>(ctx, A, s) : launch_br_wide<2, 10, 1, MODE>(ctx, A, s);
+        if (l == 3 && bg == 7) return ctx->NP == 2 ? launch_br_wide<3, 7, 2, MODE>(ctx, A, s) : launch_br_wide<3, 7, 1, MODE>(ctx, A, s);
+        return fail(ctx, TFHE_B200_EINVAL, "unsupported (l, bgbit)");
+    }
     if (l == 2 && bg == 10) return ctx->NP == 2 ? launch_br_np<2, 10, 2, MODE>(ctx, A, s) : launch_br_np<2, 10, 1, MODE>(ctx, A, s);
     if (l == 3 && bg == 7) return ctx->NP == 2 ? launch_br_np<3, 7, 2, MODE>(ctx, A, s) : launch_br_np<3, 7, 1, MODE>(ctx, A, s);
     return fail(ctx, TFHE_B200_EINVAL, "unsupported (l, bgbit)");
@@ -236,6 +267,11 @@ int launch_br(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
 int launch_extern(tfhe_b200_ctx* ctx, const int32_t* acc, const int32_t* idx, int32_t* out, size_t count, cudaStream_t s) {
     const int l = ctx->P.l, bg = ctx->P.bgbit;
     if (count == 0) return 0;
+    if (ctx->P.k > 1) {
+        if (l == 2 && bg == 10) return ctx->NP == 2 ? launch_extern_wide<2, 10, 2>(ctx, acc, idx, out, count, s) : launch_extern_wide<2, 10, 1>(ctx, acc, idx, out, count, s);
+        if (l == 3 && bg == 7) return ctx->NP == 2 ? launch_extern_wide<3, 7, 2>(ctx, acc, idx, out, count, s) : launch_extern_wide<3, 7, 1>(ctx, acc, idx, out, count, s);
+        return fail(ctx, TFHE_B200_EINVAL, "unsupported (l, bgbit)");
+    }
     unsigned grid = (unsigned)count;
     if (l == 2 && bg == 10) {
         if (ctx->NP == 2) extern_product_kernel<2, 10, 2><<<grid, 64, 0, s>>>(ctx->d_bk_fft, ctx->d_E, acc, idx, out);
@@ -406,7 +442,8 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
     if (!params || !out) return fail(nullptr, TFHE_B200_EINVAL, "null argument");
     *out = nullptr;
     const auto& P = *params;
-    if (P.N != 1024 || P.k != 1) return fail(nullptr, TFHE_B200_EINVAL, "only N = 1024, k = 1 are supported");
+    if (P.N != 1024 || P.k < 1 || P.k > 3) return fail(nullptr, TFHE_B200_EINVAL, "only N = 1024, k = 1..3 are supported");
+    if (P.parties != 1 && P.k != 1) return fail(nullptr, TFHE_B200_EINVAL, "MK-TFHE is defined for k = 1 (mk_internals.jl:48)");
     if (P.n < 1 || P.n > 4096) return fail(nullptr, TFHE_B200_EINVAL, "n out of range");
     if (P.t < 1 || P.basebit < 1 || P.t * P.basebit > 31 || P.basebit > 4 || P.n > 4000)
         return fail(nullptr, TFHE_B200_EINVAL, "bad keyswitch parameters (the reference's sets use t = 8, basebit = 2)");
@@ -426,7 +463,7 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
     c->cluster = env_int("TFHE_B200_CLUSTER", 1);
     c->ks_tile = env_int("TFHE_B200_KS_TILE", 1);
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) c->sm_count = prop.multiProcessorCount; }
-    if (c->cluster && c->NP == 2 && P.parties <= 1) {
+    if (c->cluster && c->NP == 2 && P.parties <= 1 && P.k == 1) {
         // how many two-CTA clusters of the latency kernel the device can hold at once (0 on a device or partition that
         // cannot co-schedule CTA pairs with this much shared memory: the one-CTA latency kernel takes over)
         auto probe = [&](auto kern, int threads, size_t smem) {
@@ -537,7 +574,7 @@ int tfhe_b200_load_bk(tfhe_b200_ctx* ctx, const int32_t* bk) {
     if (!ctx || !bk) return TFHE_B200_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (ctx->P.parties != 1) return fail(ctx, TFHE_B200_EINVAL, "use tfhe_b200_mk_load_bk on an MK context");
-    return load_bk_polys(ctx, bk, (size_t)ctx->P.n * ctx->P.l * 4);
+    return load_bk_polys(ctx, bk, (size_t)ctx->P.n * ctx->P.l * (ctx->P.k + 1) * (ctx->P.k + 1));
 }
 
 static int load_ksk_sets(tfhe_b200_ctx* ctx, const int32_t* ksk, int sets) {
@@ -721,8 +758,9 @@ int tfhe_b200_extern_product_batch(tfhe_b200_ctx* ctx, const int32_t* acc, const
     for (size_t g = 0; g < count; g++)
         if (bk_index[g] < 0 || bk_index[g] >= ctx->P.n) return fail(ctx, TFHE_B200_EINVAL, "bk_index out of range");
     const int32_t* hin[3] = {acc, bk_index, nullptr};
-    const size_t win[3] = {2 * (size_t)kN, 1, 0};
-    return host_chunks(ctx, hin, win, out, 2 * (size_t)kN, count, [&](int32_t* dacc, int32_t* didx, int32_t*, int32_t* dout, size_t cnt) {
+    const size_t wacc = (size_t)(ctx->P.k + 1) * kN;
+    const size_t win[3] = {wacc, 1, 0};
+    return host_chunks(ctx, hin, win, out, wacc, count, [&](int32_t* dacc, int32_t* didx, int32_t*, int32_t* dout, size_t cnt) {
         return launch_extern(ctx, dacc, didx, dout, cnt, ctx->stream);
     });
 }
@@ -736,8 +774,9 @@ int tfhe_b200_blind_rotate_batch(tfhe_b200_ctx* ctx, const int32_t* acc_in, cons
     if (!acc_in || !bara || !acc_out) return fail(ctx, TFHE_B200_EINVAL, "null argument");
     if (n_iter < 0 || n_iter > ctx->P.n) return fail(ctx, TFHE_B200_EINVAL, "n_iter out of range");
     const int32_t* hin[3] = {acc_in, bara, nullptr};
-    const size_t win[3] = {2 * (size_t)kN, (size_t)ctx->P.n, 0};
-    return host_chunks(ctx, hin, win, acc_out, 2 * (size_t)kN, count, [&](int32_t* dacc, int32_t* dbara, int32_t*, int32_t* dout, size_t cnt) {
+    const size_t wacc = (size_t)(ctx->P.k + 1) * kN;
+    const size_t win[3] = {wacc, (size_t)ctx->P.n, 0};
+    return host_chunks(ctx, hin, win, acc_out, wacc, count, [&](int32_t* dacc, int32_t* dbara, int32_t*, int32_t* dout, size_t cnt) {
         BlindRotateArgs A = br_args(ctx, cnt);
         A.acc_in = dacc; A.bara_in = dbara; A.n_iter = n_iter; A.out = dout;
         return launch_br<1>(ctx, A, ctx->stream);

@@ -208,17 +208,18 @@ __global__ void __launch_bounds__(64) extern_product_kernel(const double2* __res
 // K1: exact negacyclic product of two arbitrary int32 polynomials mod 2^32.
 // x = xh*2^16 + xl, y = yh*2^16 + yl (signed 16-bit pieces):  x*y = xl*yl + 2^16 (xh*yl + xl*yh)  (mod 2^32)
 // Rounded magnitudes <= 2^41, error bound < 0.03.
-// x_stride: distance in words between consecutive x operands (kN; 0 = the same x for every product, e.g. the TLWE key)
+// x_stride: distance in words between consecutive x operands (kN; 0 = the same x for every product, e.g. the TLWE key);
+// y_stride / out_stride likewise (k * kN when the operands are one mask polynomial of TLWE samples with k of them)
 __global__ void __launch_bounds__(64) polymul_kernel(const int32_t* __restrict__ xs, const int32_t* __restrict__ ys,
                                                      int32_t* __restrict__ out, const double2* __restrict__ E,
-                                                     size_t x_stride = kN) {
+                                                     size_t x_stride = kN, size_t y_stride = kN, size_t out_stride = kN) {
     __shared__ double2 X1[512];
     __shared__ double2 X2[kX2Elems];
     __shared__ double2 SX[2][512];   // spectra of xl, xh
     const int t = threadIdx.x;
     Twiddles w; w.load(E, t);
     const int32_t* x = xs + (size_t)blockIdx.x * x_stride;
-    const int32_t* y = ys + (size_t)blockIdx.x * kN;
+    const int32_t* y = ys + (size_t)blockIdx.x * y_stride;
     double2 a[8];
 #pragma unroll 1
     for (int pc = 0; pc < 2; pc++) {
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(64) polymul_kernel(const int32_t* __restrict__
     __syncthreads();
     fft512_inverse(p1, w, X1, X2, t, 0);
     fft512_inverse(p2, w, X1, X2, t, 0);
-    int32_t* o = out + (size_t)blockIdx.x * kN;
+    int32_t* o = out + (size_t)blockIdx.x * out_stride;
 #pragma unroll
     for (int m = 0; m < 8; m++) {
         o[t + 64 * m] = (int32_t)(round_to_u32_fast<true>(p1[m].x) + (round_to_u32_fast<true>(p2[m].x) << 16));

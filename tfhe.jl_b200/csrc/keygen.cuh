@@ -134,19 +134,25 @@ __global__ void lwe_phase_kernel(const int32_t* __restrict__ key, int key_len, c
     }
 }
 
-// tgsw_encrypt (tgsw.jl:84-88) from its parts: sample s = (i, r, j) of the key is the TLWE pair (a_s, noise_s + S (*) a_s)
-// (tlwe.jl:63-73, k = 1) plus lwe_key[i] * 2^(32 - (r+1)*bgbit) on coefficient 0 of component j (tgsw.jl:62-69).
-// bk layout [n][l][2][2][N].
+// tgsw_encrypt (tgsw.jl:84-88) from its parts: sample s = (i, r, j) of the key is the TLWE sample
+// (a_s1..a_sk, noise_s + sum_c S_c (*) a_sc) (tlwe.jl:63-73) plus lwe_key[i] * 2^(32 - (r+1)*bgbit) on coefficient 0 of
+// component j (tgsw.jl:62-69).  a, prod [S][k][N]; noise [S][N]; bk layout [n][l][k+1][k+1][N].
 __global__ void bk_assemble_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ prod, const int32_t* __restrict__ noise,
-                                   const int32_t* __restrict__ lwe_key, int32_t* __restrict__ bk, int l, int bgbit) {
-    const size_t s = blockIdx.x;                 // sample index (i*l + r)*2 + j
-    const int j = (int)(s & 1), r = (int)((s >> 1) % l), i = (int)((s >> 1) / l);
+                                   const int32_t* __restrict__ lwe_key, int32_t* __restrict__ bk, int l, int bgbit, int k) {
+    const size_t s = blockIdx.x;                 // sample index (i*l + r)*(k+1) + j
+    const int j = (int)(s % (k + 1)), r = (int)((s / (k + 1)) % l), i = (int)((s / (k + 1)) / l);
     const uint32_t g = (uint32_t)lwe_key[i] << (32 - (r + 1) * bgbit);
-    int32_t* o = bk + s * 2 * kN;
+    int32_t* o = bk + s * (size_t)(k + 1) * kN;
     for (int x = threadIdx.x; x < kN; x += blockDim.x) {
-        uint32_t va = (uint32_t)a[s * kN + x], vb = (uint32_t)noise[s * kN + x] + (uint32_t)prod[s * kN + x];
-        if (x == 0) { if (j == 0) va += g; else vb += g; }
-        o[x] = (int32_t)va; o[kN + x] = (int32_t)vb;
+        uint32_t vb = (uint32_t)noise[s * kN + x];
+        for (int c = 0; c < k; c++) {
+            uint32_t va = (uint32_t)a[(s * k + c) * kN + x];
+            vb += (uint32_t)prod[(s * k + c) * kN + x];
+            if (x == 0 && j == c) va += g;
+            o[c * kN + x] = (int32_t)va;
+        }
+        if (x == 0 && j == k) vb += g;
+        o[k * kN + x] = (int32_t)vb;
     }
 }
 
