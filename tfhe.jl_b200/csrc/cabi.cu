@@ -45,6 +45,8 @@ struct tfhe_b200_ctx {
     int G = 0;                       // gates per CTA of the blind-rotation kernel (0 = default, see launch_br_np)
     int sm_count = 148;
     int l2_hint = 0;                 // TFHE_B200_L2HINT=1: key chunks fetched with the L2 evict_last policy (K3 with the producer warpgroup)
+    int l2_persist = 0;              // TFHE_B200_L2PERSIST=pct: K3 launches carry an access-policy window over the key (hit ratio pct/100, persisting L2 set-aside at its maximum)
+    size_t bk_bytes = 0;             // size of d_bk_fft
     int max_clusters = 0;            // two-CTA clusters of the latency kernel the device holds at once (cudaOccupancyMaxActiveClusters)
     int cluster = 1;                 // batches of <= 1 gate per two SMs (two-piece 80-bit set) take the two-CTA cluster kernel; TFHE_B200_CLUSTER=0: off, 2: phase probe
     int lowlat = 1;                  // batches of <= 1 gate per SM: one gate per CTA spread over 4 groups + sliced key switch
@@ -125,6 +127,20 @@ int launch_br_g(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
     if (smem > 227 * 1024) return fail(ctx, TFHE_B200_EINVAL, "LWE dimension too large for the shared-memory layout");
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned grid = (unsigned)((A.count + G - 1) / G);
+    if (ctx->l2_persist > 0 && ctx->bk_bytes) {
+        // experiment: keep the key in the persisting part of L2 instead of re-streaming 40 % of it from DRAM per wave
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        at[0].val.accessPolicyWindow.base_ptr = (void*)A.bk_fft;
+        at[0].val.accessPolicyWindow.num_bytes = ctx->bk_bytes;
+        at[0].val.accessPolicyWindow.hitRatio = std::min(1.0f, ctx->l2_persist / 100.0f);
+        at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(64 * G + ((OPT >> 7) & 1) * 128); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CU(cudaLaunchKernelEx(&cfg, kern, A));
+    } else
     kern<<<grid, 64 * G + ((OPT >> 7) & 1) * 128, smem, s>>>(A);
     CU(cudaGetLastError());
     ctx->launches++;
@@ -460,9 +476,20 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
     c->mk_pw = env_int("TFHE_B200_MK_PW", 1);
     c->lowlat = env_int("TFHE_B200_LOWLAT", 1);
     c->l2_hint = env_int("TFHE_B200_L2HINT", 0);
+    c->l2_persist = env_int("TFHE_B200_L2PERSIST", 0);
     c->cluster = env_int("TFHE_B200_CLUSTER", 1);
     c->ks_tile = env_int("TFHE_B200_KS_TILE", 1);
-    { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) c->sm_count = prop.multiProcessorCount; }
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) {
+            c->sm_count = prop.multiProcessorCount;
+            if (c->l2_persist > 0) {
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize) != cudaSuccess) { cudaGetLastError(); c->l2_persist = 0; }
+                if (env_int("TFHE_B200_VERBOSE", 0))
+                    fprintf(stderr, "tfhe_b200: L2 %d MB, persisting max %d MB, window max %d MB\n", prop.l2CacheSize >> 20, prop.persistingL2CacheMaxSize >> 20, prop.accessPolicyMaxWindowSize >> 20);
+            }
+        }
+    }
     if (c->cluster && c->NP == 2 && P.parties <= 1 && P.k == 1) {
         // how many two-CTA clusters of the latency kernel the device can hold at once (0 on a device or partition that
         // cannot co-schedule CTA pairs with this much shared memory: the one-CTA latency kernel takes over)
@@ -548,6 +575,7 @@ static int load_bk_polys(tfhe_b200_ctx* ctx, const int32_t* bk, size_t polys) {
     CU(cudaSetDevice(ctx->device));
     if (ctx->d_bk_fft) { CU(cudaFree(ctx->d_bk_fft)); ctx->d_bk_fft = nullptr; }
     CU(cudaMalloc(&ctx->d_bk_fft, polys * ctx->NP * kSpectrum * sizeof(double2)));
+    ctx->bk_bytes = polys * ctx->NP * kSpectrum * sizeof(double2);
     // transform in slabs so the int32 staging buffer stays small
     const size_t slab = 1 << 14;
     int32_t* d_tmp = nullptr;
