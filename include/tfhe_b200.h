@@ -137,6 +137,8 @@ int tfhe_b200_blind_rotate_batch(tfhe_b200_ctx* ctx, const int32_t* acc_in, cons
 int tfhe_b200_polymul_batch(tfhe_b200_ctx* ctx, const int32_t* x, const int32_t* y, int32_t* out, size_t count);
 
 /* ---- single-key hot path, device buffers (asynchronous on `stream`) ------------------------ */
+/* A batch of any size: it is walked in pieces of ~2^20 gates (whole CTA waves) so that the library's scratch (the
+ * extracted samples between blind rotation and key switch, 4 KB per gate) stays below 9 GB of the 180 GB. */
 int tfhe_b200_gate_batch_dev(tfhe_b200_ctx* ctx, int op, const int32_t* x, const int32_t* y, const int32_t* z,
                              int32_t* out, size_t count, void* stream);
 int tfhe_b200_bootstrap_wo_ks_batch_dev(tfhe_b200_ctx* ctx, int32_t mu, const int32_t* x, int32_t* out,

@@ -362,3 +362,34 @@ def test_pageable_and_unaligned_host_buffers(keys80, gctx80):
     out = gctx80.gate(O.AND, x, y)
     assert np.array_equal(out, np.tile(out[:64], (count // 64 + 1, 1))[:count])
     assert np.array_equal(out[:8], O.Context(keys80).gate(O.AND, x[:8], y[:8]))
+
+
+def test_device_resident_batch_is_walked_in_pieces(keys80_small, octx80_small, monkeypatch):
+    """tfhe_b200_gate_batch_dev bounds its scratch (the extracted samples between blind rotation and key switch) by walking
+    a large device-resident batch in pieces of whole CTA waves (2^20 gates by default).  With the piece size forced down
+    to one wave, a ragged 1 500-gate NAND / MUX batch must give the ciphertexts of the one-pass run and of the oracle."""
+    import torch
+    P = keys80_small.params
+    count = 1500
+    bits = np.random.default_rng(31).integers(0, 2, (count, 3)).astype(bool)
+    rng = O.Rng(31)
+    cts = [O.encrypt(rng, keys80_small, bits[:, i]) for i in range(3)]
+    d = [torch.from_numpy(c).cuda() for c in cts]
+    s = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for piece in (None, "1"):
+        if piece:
+            monkeypatch.setenv("TFHE_B200_DEV_PIECE", piece)     # clamped up to one wave of 4 x SM count gates
+        ctx = T.Context(n=P.n, l=P.l, bgbit=P.bgbit, t=P.t, basebit=P.basebit)
+        ctx.load_bk(keys80_small.bk); ctx.load_ksk(keys80_small.ksk)
+        res = []
+        for op, nargs in ((O.NAND, 2), (O.MUX, 3)):
+            out = torch.empty_like(d[0])
+            ptrs = [d[i].data_ptr() if i < nargs else 0 for i in range(3)]
+            ctx.gate_dev(op, ptrs[0], ptrs[1], ptrs[2], out.data_ptr(), count, stream=s)
+            torch.cuda.synchronize()
+            res.append(out.cpu().numpy())
+        outs.append(res)
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[1][0], octx80_small.gate(O.NAND, cts[0], cts[1]))
+    assert np.array_equal(outs[1][1][:200], octx80_small.gate(O.MUX, cts[0][:200], cts[1][:200], cts[2][:200]))

@@ -72,6 +72,7 @@ struct tfhe_b200_ctx {
     std::mutex mu;
     std::atomic<uint64_t> launches{0};
     size_t chunk = 1 << 16;          // gates per host-staged chunk
+    size_t dev_piece = (size_t)1 << 20;   // gates per pass of a device-resident batch (bounds the scratch; TFHE_B200_DEV_PIECE)
 };
 
 namespace {
@@ -512,6 +513,7 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
     {   // gates per host-staged chunk: at least one wave of CTAs, never zero or negative
         const long long v = env_int("TFHE_B200_CHUNK", 1 << 16);
         c->chunk = (size_t)std::max<long long>(v, (long long)4 * c->sm_count);
+        c->dev_piece = (size_t)std::max<long long>(env_int("TFHE_B200_DEV_PIECE", 1 << 20), (long long)4 * c->sm_count);
     }
     ctx = c;
     cudaError_t e = cudaEventCreateWithFlags(&c->scratch_ev, cudaEventDisableTiming);
@@ -635,10 +637,20 @@ int tfhe_b200_gate_batch_dev(tfhe_b200_ctx* ctx, int op, const int32_t* x, const
     std::lock_guard<std::mutex> lk(ctx->mu);
     int rc = check_single(ctx, true, true);
     if (rc) return rc;
-    const size_t wu = (size_t)ctx->P.N * ctx->P.k + 1;
-    if ((rc = reserve(ctx, ctx->bu1, (op == TFHE_B200_MUX ? 2 : 1) * count * wu * 4))) return rc;
+    const size_t w = (size_t)ctx->P.n + 1, wu = (size_t)ctx->P.N * ctx->P.k + 1;
+    // The extracted samples between blind rotation and key switch (4 KB per gate, 8 KB for MUX) live in a scratch buffer:
+    // a device-resident batch of any size is walked in pieces of ~2^20 gates (whole CTA waves) so that the scratch stays
+    // below 9 GB however large the batch is (16 M gates would otherwise need 66 GB next to their 96 GB of ciphertexts)
+    const size_t wave = (size_t)4 * ctx->sm_count, piece = std::max<size_t>(wave, ctx->dev_piece / wave * wave);
+    if ((rc = reserve(ctx, ctx->bu1, (op == TFHE_B200_MUX ? 2 : 1) * std::min(count, piece) * wu * 4))) return rc;
     ScratchGuard guard(ctx, (cudaStream_t)stream);
-    return gate_dev(ctx, op, x, y, z, out, count, (int32_t*)ctx->bu1.p, (cudaStream_t)stream);
+    if (count == 0) return gate_dev(ctx, op, x, y, z, out, 0, (int32_t*)ctx->bu1.p, (cudaStream_t)stream);   // argument checks only
+    for (size_t off = 0; off < count; off += piece) {
+        const size_t cnt = std::min(piece, count - off);
+        if ((rc = gate_dev(ctx, op, x ? x + off * w : nullptr, y ? y + off * w : nullptr, z ? z + off * w : nullptr, out + off * w, cnt,
+                           (int32_t*)ctx->bu1.p, (cudaStream_t)stream))) return rc;
+    }
+    return 0;
 }
 
 int tfhe_b200_bootstrap_wo_ks_batch_dev(tfhe_b200_ctx* ctx, int32_t mu, const int32_t* x, int32_t* out, size_t count,

@@ -19,6 +19,7 @@ if [ "${EXTRA:-1}" = "1" ]; then
   SAMPLE=4 timeout 300 python tools/mk_perf.py 4 1184 > gpurun_out/mk_perf_p4.json 2>> gpurun_out/mk_perf.err
   timeout 300 python tools/latency128.py > gpurun_out/latency128.json 2> gpurun_out/latency128.err
   timeout 900 python tools/sweep.py > gpurun_out/sweep.json 2> gpurun_out/sweep.err
+  timeout 300 python tools/mask_size_perf.py > gpurun_out/mask_size.json 2> gpurun_out/mask_size.err
 fi
 NCU="ncu --set full --import-source on --clock-control none -f"
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras"   # the default workload (2^17 gates per launch)
