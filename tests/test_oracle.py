@@ -193,3 +193,47 @@ def test_tutorial_minimum_is_42(keys80, octx80):
     res = octx80.gate(O.MUX, sel, b, a)                         # tutorial.jl:61
     bits = O.decrypt(keys80, res)
     assert sum(int(v) << i for i, v in enumerate(bits)) == 42   # tutorial.jl:77
+
+
+# ---- tlwe_mask_size > 1 (api.jl:30,55): the oracle's loops over k+1 against an independent statement ----
+def _with_k(base, k, n):
+    return O.Params(n, base.lwe_sigma, base.N, k, base.l, base.bgbit, base.bs_sigma, base.t, base.basebit, base.ks_sigma, 1)
+
+
+@pytest.mark.parametrize("k", [2, 3])
+def test_extern_product_mask_size_gt1_matches_definition(k):
+    """tgsw_extern_mul (tgsw.jl:125-129) restated from the definition in numpy + Python integers:
+    out_c' = sum_{c, r} digit_r(acc_c) (*) BK[i][r][c][c'], digits from tgsw.jl:99-117."""
+    P = _with_k(O.PARAMS_80, k, 3)
+    keys = O.keygen(P, 11 + k)
+    octx = O.Context(keys)
+    rng = np.random.default_rng(k)
+    acc = random_torus(rng, k + 1, N)
+    l, bg = P.l, P.bgbit
+    offset = sum(1 << (32 - r * bg) for r in range(1, l + 1)) * (1 << (bg - 1))
+    want = np.zeros((k + 1, N), dtype=np.int64)
+    for c in range(k + 1):
+        u = (acc[c].astype(np.int64) + offset) & 0xFFFFFFFF
+        for r in range(l):
+            digit = (((u >> (32 - (r + 1) * bg)) & ((1 << bg) - 1)) - (1 << (bg - 1))).astype(np.int32)
+            for c2 in range(k + 1):
+                want[c2] += exact_negacyclic(digit, keys.bk[1, r, c, c2]).astype(np.int64)
+    want = (((want + 2 ** 31) % 2 ** 32) - 2 ** 31).astype(np.int32)
+    assert np.array_equal(octx.extern_mul(1, acc, O.ROUTE_EXACT), want)
+    assert np.array_equal(octx.extern_mul(1, acc, O.ROUTE_FFT), want)
+
+
+def test_gate_truth_tables_mask_size_2(keys80):
+    """Full-size 80-bit set with two mask polynomials: NAND / XOR / MUX decrypt to their truth tables and the phases stay
+    inside the 1/16 contract of gates.jl:1-6 (a wrong index order anywhere in the k+1 loops would not)."""
+    keys = O.keygen(_with_k(O.PARAMS_80, 2, 500), 77)
+    octx = O.Context(keys)
+    bits = np.array(list(itertools.product([False, True], repeat=3)))
+    rng = O.Rng(52)
+    x, y, z = (O.encrypt(rng, keys, bits[:, i]) for i in range(3))
+    nand = octx.gate(O.NAND, x, y)
+    assert np.array_equal(O.decrypt(keys, nand), ~(bits[:, 0] & bits[:, 1]))
+    assert np.array_equal(O.decrypt(keys, octx.gate(O.XOR, x, y)), bits[:, 0] ^ bits[:, 1])
+    assert np.array_equal(O.decrypt(keys, octx.gate(O.MUX, x, y, z)), np.where(bits[:, 0], bits[:, 1], bits[:, 2]))
+    ph = O.phase(keys, nand).astype(np.float64) / 2 ** 32
+    assert np.abs(np.abs(ph) - 0.125).max() < 1 / 16
