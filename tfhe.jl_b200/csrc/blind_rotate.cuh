@@ -554,6 +554,10 @@ struct BlindRotateArgs {
     int32_t* out;            // MODE 0: [count][N+1] extracted LWE; MODE 1: [count][2][N]
     int n, n_iter, n_pad;
     unsigned long long count;
+    // K3 gate -> CTA map: the first `split` CTAs hold G gates each, every later CTA `tail` (<= G) gates.  The launcher makes
+    // the LAST wave of CTAs carry fewer gates each instead of leaving SMs idle (groups without a gate do no work, so such a
+    // CTA finishes sooner): 1 024 gates = one wave of 148 x 4 + one wave of 148 x 3 instead of 148 x 4 + 108 x 4.
+    unsigned split; int tail;
     unsigned long long* probe;   // development: clock64 phase probe of the OPT bit-3 kernel variants (else null)
     int l2_hint;                 // 1: key chunks are fetched with the L2 evict_last policy
 };
@@ -604,8 +608,13 @@ __global__ void __launch_bounds__(64 * G + ((OPT >> 7) & 1) * 128, 1) blind_rota
     uint64_t* empty = full + STAGES;
     unsigned char* groups = smem_raw + (size_t)STAGES * kChunkBytes + 128;
 
+    // gates of this CTA (see BlindRotateArgs::split): groups beyond them do nothing and are not waited for by the ring
+    const int cta_gates = blockIdx.x < A.split ? G : A.tail;
+    const unsigned long long g_first = blockIdx.x < A.split ? (unsigned long long)blockIdx.x * G
+                                                            : (unsigned long long)A.split * G + (unsigned long long)(blockIdx.x - A.split) * A.tail;
+    const int n_valid = (int)(A.count - g_first < (unsigned long long)cta_gates ? A.count - g_first : (unsigned long long)cta_gates);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 2 * G); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 2 * n_valid); }   // one arrival per consuming warp
         mbar_fence_init();
     }
     __syncthreads();
@@ -638,13 +647,11 @@ __global__ void __launch_bounds__(64 * G + ((OPT >> 7) & 1) * 128, 1) blind_rota
     double2* X2 = X1 + (TM == 3 ? 2 : 1) * kSpectrum;
     int32_t* acc = reinterpret_cast<int32_t*>(X2 + kX2Elems);
     int32_t* bara = acc + 2 * kN;
-    const unsigned long long g = (unsigned long long)blockIdx.x * G + grp;
-    const bool valid = g < A.count;   // a group without a gate still walks the ring (on zeros) to keep the lockstep
+    const unsigned long long g = g_first + grp;
+    const bool valid = grp < n_valid;   // a group without a gate skips the walk (the ring's empty barriers count the valid groups only)
     typename std::conditional<TM == 3, TwiddlesFull, Twiddles>::type w; w.load(A.E, t);
 
     if (!valid) {
-        for (int x = t; x < 2 * kN; x += 64) acc[x] = 0;
-        for (int i = t; i < A.n_iter; i += 64) bara[i] = 0;
     } else if (MODE == 0) {
         // gate prologue (gates.jl) + modulus switch (bootstrap.jl:74-75)
         const bool second = A.half != 0 && g >= A.half;
@@ -678,8 +685,11 @@ __global__ void __launch_bounds__(64 * G + ((OPT >> 7) & 1) * 128, 1) blind_rota
     long long pr[4] = {0, 0, 0, 0};
     long long t_start = 0;
     if (PROBE) t_start = clock64();
+    // a group without a gate does not walk.  The vote makes the bound warp-uniform for the compiler: with a per-thread
+    // bound it treats the whole iteration as divergent code (WARPSYNCs, no uniform registers) and the kernel loses 5 %
+    const int n_walk = __all_sync(0xffffffffu, valid) ? A.n_iter : 0;
 #pragma unroll 1
-    for (int i = 0; i < A.n_iter; i++) {   // bootstrap.jl:19-23
+    for (int i = 0; i < n_walk; i++) {   // bootstrap.jl:19-23
         if constexpr (TM == 3 && ((OPT >> 4) & 1) && L == 2) extern_product_step_os_dual<BGBIT>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id);
         else if constexpr (TM == 3) extern_product_step_os<L, BGBIT, 1, PROBE>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id, pr);
         else if constexpr (TM != 0) extern_product_step_tmem<L, BGBIT, NP, (TM == 2 && NP == 2) ? 1 : 0>(acc, bara[i], bk, w, X1, X2, tm, t, bar_id);

@@ -50,6 +50,7 @@ struct tfhe_b200_ctx {
     int max_clusters = 0;            // two-CTA clusters of the latency kernel the device holds at once (cudaOccupancyMaxActiveClusters)
     int cluster = 1;                 // batches of <= 1 gate per two SMs (two-piece 80-bit set) take the two-CTA cluster kernel; TFHE_B200_CLUSTER=0: off, 2: phase probe
     int lowlat = 1;                  // batches of <= 1 gate per SM: one gate per CTA spread over 4 groups + sliced key switch
+    int balance_tail = 1;            // K3: the last wave spreads its gates over all SMs (TFHE_B200_BALANCE=0: full CTAs only)
     int ks_tile = 1;                 // large batches: tiled key switch (TFHE_B200_KS_TILE=0: one CTA per ciphertext)
     int mk_ring = 1;                 // MK blind rotation: 1 = TMA key ring, several gates per CTA (mk_blind_rotate.cuh)
     int mk_pw = 1;                   // MK ring kernel: dedicated producer warpgroup (TFHE_B200_MK_PW=0: in-line producer)
@@ -122,12 +123,20 @@ int env_int(const char* name, int dflt) {
 
 // ---- kernel dispatch ------------------------------------------------------------------------------
 template <int L, int BGBIT, int NP, int G, int STAGES, int MODE, int TM = 0, int OPT = 0>
-int launch_br_g(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
+int launch_br_g(tfhe_b200_ctx* ctx, const BlindRotateArgs& A_in, cudaStream_t s) {
     auto kern = blind_rotate_kernel<L, BGBIT, NP, G, STAGES, MODE, TM, OPT>;
-    const size_t smem = br_smem_bytes(NP, G, STAGES, A.n_pad, TM);
+    const size_t smem = br_smem_bytes(NP, G, STAGES, A_in.n_pad, TM);
     if (smem > 227 * 1024) return fail(ctx, TFHE_B200_EINVAL, "LWE dimension too large for the shared-memory layout");
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    unsigned grid = (unsigned)((A.count + G - 1) / G);
+    // gate -> CTA map (BlindRotateArgs::split): full waves of G gates per CTA, then ONE wave that spreads the remaining gates
+    // over all SMs (fewer gates per CTA, done sooner) instead of a partial wave of full CTAs
+    BlindRotateArgs A = A_in;
+    const unsigned long long per_wave = (unsigned long long)G * ctx->sm_count;
+    const unsigned long long full_waves = ctx->balance_tail ? (A.count - 1) / per_wave : A.count / per_wave;
+    const unsigned long long rest = A.count - full_waves * per_wave;
+    A.split = (unsigned)(full_waves * ctx->sm_count);
+    A.tail = ctx->balance_tail ? (int)std::max<unsigned long long>(1, (rest + ctx->sm_count - 1) / ctx->sm_count) : G;
+    unsigned grid = A.split + (unsigned)((rest + A.tail - 1) / A.tail);
     if (ctx->l2_persist > 0 && ctx->bk_bytes) {
         // experiment: keep the key in the persisting part of L2 instead of re-streaming 40 % of it from DRAM per wave
         cudaLaunchConfig_t cfg = {};
@@ -480,6 +489,7 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
     c->l2_persist = env_int("TFHE_B200_L2PERSIST", 0);
     c->cluster = env_int("TFHE_B200_CLUSTER", 1);
     c->ks_tile = env_int("TFHE_B200_KS_TILE", 1);
+    c->balance_tail = env_int("TFHE_B200_BALANCE", 1);
     {
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) {
