@@ -251,15 +251,20 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
         return launch_br_g<L, BGBIT, NP, 4, 6, MODE>(ctx, A, s);   // a two-piece-only variant was asked for with one piece
     }
 }
-// mask size k > 1: two gates per CTA, output spectra in shared memory, key from L2
+// mask size k > 1: four gates per CTA, output spectra in tensor memory, key from L2
 template <int L, int BGBIT, int NP, int MODE>
-int launch_br_wide(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
+int launch_br_wide(tfhe_b200_ctx* ctx, const BlindRotateArgs& A_in, cudaStream_t s) {
     const int kp1 = ctx->P.k + 1;
     auto kern = blind_rotate_wide_kernel<L, BGBIT, NP, MODE>;
-    const size_t smem = br_wide_smem_bytes(NP, kp1, A.n_pad);
+    const size_t smem = br_wide_smem_bytes(NP, kp1, A_in.n_pad);
     if (smem > 227 * 1024) return fail(ctx, TFHE_B200_EINVAL, "LWE dimension too large for the shared-memory layout");
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)((A.count + kWideGates - 1) / kWideGates), 64 * kWideGates, smem, s>>>(A, kp1);
+    BlindRotateArgs A = A_in;   // full waves of kWideGates gates per CTA, then one wave with the rest spread over all SMs
+    const unsigned long long per_wave = (unsigned long long)kWideGates * ctx->sm_count;
+    const unsigned long long full_waves = (A.count - 1) / per_wave, rest = A.count - full_waves * per_wave;
+    A.split = (unsigned)(full_waves * ctx->sm_count);
+    A.tail = (int)std::max<unsigned long long>(1, (rest + ctx->sm_count - 1) / ctx->sm_count);
+    kern<<<A.split + (unsigned)((rest + A.tail - 1) / A.tail), 64 * kWideGates, smem, s>>>(A, kp1);
     CU(cudaGetLastError());
     ctx->launches++;
     return 0;
@@ -268,7 +273,7 @@ template <int L, int BGBIT, int NP>
 int launch_extern_wide(tfhe_b200_ctx* ctx, const int32_t* acc, const int32_t* idx, int32_t* out, size_t count, cudaStream_t s) {
     const int kp1 = ctx->P.k + 1;
     auto kern = extern_product_wide_kernel<L, BGBIT, NP>;
-    const size_t smem = br_wide_smem_bytes(NP, kp1, 0, 1);
+    const size_t smem = br_wide_group_bytes(NP, kp1, 0, true);
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)count, 64, smem, s>>>(ctx->d_bk_fft, ctx->d_E, acc, idx, out, kp1);
     CU(cudaGetLastError());
