@@ -8,7 +8,7 @@
 // output spectra — 96 or 128 registers' worth too many for the register file next to a transform — accumulated in
 // TENSOR MEMORY (tmem.cuh: every thread owns a TMEM row; read-modify-write on the LDTM/STTM datapath, off the
 // shared-memory pipe; 31-35 KB of shared memory per gate instead of 78-98 KB, so four gates share an SM instead of two:
-// 21.0 k -> see DESIGN.md gates/s at k = 2).  The stand-alone external product keeps them in shared memory.
+// 21.0 k -> 34.2 k gates/s at k = 2).  The stand-alone external product keeps them in shared memory.
 // Arithmetic, summation order and rounding are those of extern_product_step (kernels.cuh): the magnitudes grow by
 // (k+1)/2 (<= 2^37 for k = 3 with two 16-bit key pieces), far inside the 2^41 the rounding trick is proven for.
 #pragma once
