@@ -130,14 +130,14 @@ def sm_count():
     return torch.cuda.get_device_properties(0).multi_processor_count
 
 
-def test_mk_keyswitch_tiled_full_size_equals_per_ciphertext_kernel_and_oracle(monkeypatch):
+@pytest.mark.parametrize("count", [4100, 4800], ids=["tiles_of_32", "tiles_of_64"])
+def test_mk_keyswitch_tiled_full_size_equals_per_ciphertext_kernel_and_oracle(monkeypatch, count):
     """mk_keyswitch (mk_internals.jl:397-411) at n = 500 (table stride 512), so that batches of 4 096 and more really
     take keyswitch_tile_kernel in its MK mode (one launch per party, non-zero in/out offsets, the joint b accumulated
     with integer atomics).  Compared with the one-CTA-per-ciphertext kernel (TFHE_B200_KS_TILE=0) on every row and
     with the oracle on the first and the last (ragged tile) rows."""
     p = 2
     mk = random_mk_keys(p, 500, 90)
-    count = 4100
     u = np.random.default_rng(5).integers(-2 ** 31, 2 ** 31, (count, p * N + 1), dtype=np.int64).astype(np.int32)
     got = make_mk_ctx(mk).keyswitch(u)
     monkeypatch.setenv("TFHE_B200_KS_TILE", "0")

@@ -293,10 +293,11 @@ def test_latency_path_can_be_disabled_and_agrees(keys80, gctx80, monkeypatch):
     assert np.array_equal(ctx.gate(O.XOR, x[:3], y[:3]), want[:3])  # 3 gates: 1 per CTA
 
 
-@pytest.mark.parametrize("count", [4096, 4161])
+@pytest.mark.parametrize("count", [2560, 2601, 4096, 4161, 4737, 4800])
 def test_tiled_keyswitch_equals_per_ciphertext_kernel(keys80, gctx80, monkeypatch, count):
-    """Large batches use keyswitch_tile_kernel (64 ciphertexts per CTA, table streamed through shared memory);
-    TFHE_B200_KS_TILE=0 selects the one-CTA-per-ciphertext kernel.  Random dimension-1024 inputs, ragged tiles."""
+    """Large batches use keyswitch_tile_kernel (table streamed through shared memory): tiles of 32 ciphertexts from 2 560
+    up to one wave of them (4 736 on 148 SMs), tiles of 64 above; TFHE_B200_KS_TILE=0 selects the one-CTA-per-ciphertext
+    kernel.  Random dimension-1024 inputs, ragged tiles."""
     rng = np.random.default_rng(count)
     u = rng.integers(-2 ** 31, 2 ** 31, (count, 1025), dtype=np.int64).astype(np.int32)
     got = gctx80.keyswitch(u)

@@ -453,13 +453,15 @@ constexpr int kKsTile = 64;      // ciphertexts per CTA
 constexpr int kKsT = 8, kKsBasebit = 2;
 __host__ __device__ inline size_t ks_tile_smem_bytes(int stride) { return 2 * (size_t)kKsT * 4 * stride * 4 + 64; }
 
-template <int STRIDE>
-__global__ void __launch_bounds__(2 * (STRIDE / 128) * 32, 1) keyswitch_tile_kernel(KeyswitchArgs A, unsigned long long count) {
+// HALVES = 2: 64 ciphertexts per CTA.  HALVES = 1: 32 per CTA, half the warps — for batches whose 64-ciphertext tiles
+// would not fill the SMs: a tile of 32 is done in about half the time, so the fixed cost of a launch drops with it.
+template <int STRIDE, int HALVES = 2>
+__global__ void __launch_bounds__(HALVES * (STRIDE / 128) * 32, 1) keyswitch_tile_kernel(KeyswitchArgs A, unsigned long long count) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr uint32_t row_bytes = STRIDE * 4;
     constexpr uint32_t stage_bytes = kKsT * 4 * row_bytes;          // 4 slots per digit position
     constexpr int cw = STRIDE / 128;                                 // warps across the columns (4 for n = 500, 5 for n = 630)
-    constexpr int nwarps = 2 * cw;
+    constexpr int nwarps = HALVES * cw;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + 2 * (size_t)stage_bytes);
     uint64_t* empty = full + 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -475,7 +477,7 @@ __global__ void __launch_bounds__(2 * (STRIDE / 128) * 32, 1) keyswitch_tile_ker
         mbar_fence_init();
     }
     __syncthreads();
-    const unsigned long long g0 = (unsigned long long)blockIdx.x * kKsTile + gh * 32;   // first ciphertext of this warp
+    const unsigned long long g0 = (unsigned long long)blockIdx.x * (32 * HALVES) + gh * 32;   // first ciphertext of this warp
     const unsigned long long gl = g0 + lane;                                            // the one whose mask this lane fetches
     const bool lane_valid = gl < count;
     const int32_t* in_l = A.in + (lane_valid ? gl : 0) * A.in_stride + A.in_offset;

@@ -51,6 +51,8 @@ struct tfhe_b200_ctx {
     int cluster = 1;                 // batches of <= 1 gate per two SMs (two-piece 80-bit set) take the two-CTA cluster kernel; TFHE_B200_CLUSTER=0: off, 2: phase probe
     int lowlat = 1;                  // batches of <= 1 gate per SM: one gate per CTA spread over 4 groups + sliced key switch
     int balance_tail = 1;            // K3: the last wave spreads its gates over all SMs (TFHE_B200_BALANCE=0: full CTAs only)
+    int ks_tile32 = 1;               // batches that do not fill the SMs with 64-ciphertext tiles take tiles of 32 (TFHE_B200_KS_TILE32=0: off)
+    int ks_tile_min = 2560;          // smallest batch that takes the tiled key switch (TFHE_B200_KS_TILE_MIN)
     int ks_tile = 1;                 // large batches: tiled key switch (TFHE_B200_KS_TILE=0: one CTA per ciphertext)
     int mk_ring = 1;                 // MK blind rotation: 1 = TMA key ring, several gates per CTA (mk_blind_rotate.cuh)
     int mk_pw = 1;                   // MK ring kernel: dedicated producer warpgroup (TFHE_B200_MK_PW=0: in-line producer)
@@ -328,19 +330,24 @@ int launch_keyswitch_sliced(tfhe_b200_ctx* ctx, const KeyswitchArgs& A, size_t c
 }
 
 int launch_keyswitch_args(tfhe_b200_ctx* ctx, const KeyswitchArgs& A, size_t count, cudaStream_t s) {
-    // large batches: 64 ciphertexts per CTA, table streamed once per CTA through shared memory (keyswitch_tile_kernel)
-    // (a tile of 64 ciphertexts takes ~3.3 ms whatever the batch; the per-ciphertext kernel needs 0.89 us per
-    // ciphertext, so the tile kernel wins from ~4 000 ciphertexts up and fills the GPU from 64 x 148)
-    if (ctx->ks_tile && A.t == kKsT && A.basebit == kKsBasebit && (A.stride == 512 || A.stride == 640) && count >= 4096) {
+    // large batches: 64 ciphertexts per CTA, table streamed once per CTA through shared memory (keyswitch_tile_kernel).
+    // Measured (tools/ks_probe.py, profiles/r2/ks_probe_v17.json): a wave of 64-ciphertext tiles takes 4.55 ms whatever the
+    // batch, a wave of 32-ciphertext tiles 2.75 ms; the per-ciphertext kernel 2.3 ms at 2 048, 3.4 ms at 3 072, 4.2 ms at
+    // 4 096 ciphertexts.  So: one CTA per ciphertext below 2 560, tiles of 32 while one wave of them holds the batch
+    // (32 x SMs = 4 736), tiles of 64 above.
+    if (ctx->ks_tile && A.t == kKsT && A.basebit == kKsBasebit && (A.stride == 512 || A.stride == 640) && count >= (size_t)ctx->ks_tile_min) {
         const size_t smem = ks_tile_smem_bytes(A.stride);
-        const unsigned grid = (unsigned)((count + kKsTile - 1) / kKsTile);
-        if (A.stride == 512) {
-            CU(cudaFuncSetAttribute(keyswitch_tile_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            keyswitch_tile_kernel<512><<<grid, 256, smem, s>>>(A, count);
-        } else {
-            CU(cudaFuncSetAttribute(keyswitch_tile_kernel<640>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            keyswitch_tile_kernel<640><<<grid, 320, smem, s>>>(A, count);
-        }
+        const bool small = ctx->ks_tile32 && count <= (size_t)32 * ctx->sm_count;
+        const unsigned tile = small ? 32 : kKsTile, grid = (unsigned)((count + tile - 1) / tile);
+        auto go = [&](auto kern, int threads) -> int {
+            CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, threads, smem, s>>>(A, count);
+            return 0;
+        };
+        int rc;
+        if (A.stride == 512) rc = small ? go(keyswitch_tile_kernel<512, 1>, 128) : go(keyswitch_tile_kernel<512, 2>, 256);
+        else rc = small ? go(keyswitch_tile_kernel<640, 1>, 160) : go(keyswitch_tile_kernel<640, 2>, 320);
+        if (rc) return rc;
         CU(cudaGetLastError());
         ctx->launches++;
         return 0;
@@ -494,6 +501,9 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
     c->l2_persist = env_int("TFHE_B200_L2PERSIST", 0);
     c->cluster = env_int("TFHE_B200_CLUSTER", 1);
     c->ks_tile = env_int("TFHE_B200_KS_TILE", 1);
+    c->ks_tile32 = env_int("TFHE_B200_KS_TILE32", 1);
+    c->ks_tile_min = std::max(1, env_int("TFHE_B200_KS_TILE_MIN", 2560));
+    if (!c->ks_tile32) c->ks_tile_min = std::max(c->ks_tile_min, 4096);
     c->balance_tail = env_int("TFHE_B200_BALANCE", 1);
     {
         cudaDeviceProp prop;
