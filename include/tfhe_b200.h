@@ -18,9 +18,10 @@
  *     cudaStream_t passed as void* (NULL = default stream); they are asynchronous and stream-ordered:
  *     the library's scratch buffers are shared by all calls of a context, and a call given a different
  *     stream than the previous one first waits (on the device) for that call's work.
- *   - the kernel shape is chosen per call from `count`: up to 3 gates per SM a latency kernel (one gate per
- *     CTA) and a sliced key switch, above that 4 gates per CTA, from 4 096 ciphertexts a tiled key switch;
- *     the results do not depend on the choice.
+ *   - the kernel shape is chosen per call from `count`: up to one gate per two SMs a cluster of two CTAs per gate,
+ *     up to 3 gates per SM a latency kernel (one gate per CTA) and a sliced key switch, above that 4 gates per CTA
+ *     (the last wave of CTAs carries fewer), from 2 560 ciphertexts a tiled key switch; the results do not depend on
+ *     the choice.
  *   - there is NO CPU fallback: without a CUDA device every call fails with TFHE_B200_ENODEV.
  *   - calls on one context are serialised by an internal mutex; contexts are independent
  *     (one context per GPU; gate batches shard across contexts with no collective: tfhe_b200_multi_* below).

@@ -709,8 +709,8 @@ static int host_chunks(tfhe_b200_ctx* ctx, const int32_t* const hin[3], const si
     // a batch that fits one chunk is still cut in (up to) 4 pieces of whole CTA waves so that its copies overlap too
     const size_t wave = (size_t)4 * ctx->sm_count;
     size_t chunk = ctx->chunk;
-    // ... but never in more pieces than the tiled key switch has waves of CTAs (a tile of 64 ciphertexts takes 3.3 ms however
-    // few tiles a launch holds): 16 384 gates go in 2 pieces, not 4 (4 launches of 65 tiles cost 13.2 ms, 2 of 130 cost 6.6)
+    // ... but never in more pieces than the tiled key switch has waves of CTAs (a wave of 64-ciphertext tiles takes 4.55 ms however
+    // few tiles it holds): 16 384 gates go in 2 pieces, not 4 (4 launches of 65 tiles cost 18 ms, 2 of 130 cost 9)
     if (count <= chunk && count >= 8 * wave) {
         const size_t ks_wave = (size_t)kKsTile * ctx->sm_count;
         const size_t pieces = std::min<size_t>(4, std::max<size_t>(1, (count + ks_wave - 1) / ks_wave));
