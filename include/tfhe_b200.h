@@ -19,7 +19,7 @@
  *     the library's scratch buffers are shared by all calls of a context, and a call given a different
  *     stream than the previous one first waits (on the device) for that call's work.
  *   - the kernel shape is chosen per call from `count`: up to one gate per two SMs a cluster of two CTAs per gate,
- *     up to 3 gates per SM a latency kernel (one gate per CTA) and a sliced key switch, above that 4 gates per CTA
+ *     up to 2 gates per SM a latency kernel (one gate per CTA) and a sliced key switch, above that up to 4 gates per CTA
  *     (the last wave of CTAs carries fewer), from 2 560 ciphertexts a tiled key switch; the results do not depend on
  *     the choice.
  *   - there is NO CPU fallback: without a CUDA device every call fails with TFHE_B200_ENODEV.

@@ -241,12 +241,12 @@ def test_api_mirror_truth_tables():
 
 
 @pytest.mark.parametrize("flags", [_cabi.FLAG_SPLIT_FFT, _cabi.FLAG_UNSPLIT_FFT], ids=["split", "unsplit"])
-@pytest.mark.parametrize("count", [3, 37, 38, 74, 75, 148, 149, 444, 445, 601, 700, 1024, 1185])
+@pytest.mark.parametrize("count", [3, 37, 38, 74, 75, 148, 149, 296, 297, 444, 445, 601, 700, 1024, 1185])
 def test_every_batch_size_dispatch_path_equals_oracle(keys80_small, octx80_small, flags, count):
     """The library picks a kernel shape by batch size: up to one gate per two SMs (two-piece transform) a cluster of two
-    CTAs per gate (37 MUX gates = 74 bootstraps is the last such batch, 74 NAND gates likewise), up to 3 gates per SM
-    the latency kernel (one gate per CTA spread over 4 groups, 1-3 waves) + sliced key switch, above that four gates per
-    CTA.  With a short LWE key (n = 24) the oracle can check EVERY ciphertext of every path; 445 / 601 leave the last
+    CTAs per gate (37 MUX gates = 74 bootstraps is the last such batch, 74 NAND gates likewise), up to 2 gates per SM
+    (1 with the one-piece transform) the latency kernel (one gate per CTA spread over 4 groups) + sliced key switch, above
+    that up to four gates per CTA.  With a short LWE key (n = 24) the oracle can check EVERY ciphertext of every path; 445 / 601 leave the last
     CTA ragged; from 593 gates up the last wave of CTAs carries fewer gates per CTA (700: 148 x 4 + 108 x 1, 1 024:
     148 x 4 + 144 x 3, 1 185: two full waves + one gate; MUX doubles the bootstraps)."""
     P = keys80_small.params

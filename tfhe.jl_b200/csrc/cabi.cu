@@ -49,6 +49,7 @@ struct tfhe_b200_ctx {
     size_t bk_bytes = 0;             // size of d_bk_fft
     int max_clusters = 0;            // two-CTA clusters of the latency kernel the device holds at once (cudaOccupancyMaxActiveClusters)
     int cluster = 1;                 // batches of <= 1 gate per two SMs (two-piece 80-bit set) take the two-CTA cluster kernel; TFHE_B200_CLUSTER=0: off, 2: phase probe
+    int lowlat_waves = 2;            // batches of up to this many gates per SM take the latency kernel (TFHE_B200_LOWLAT_WAVES)
     int lowlat = 1;                  // batches of <= 1 gate per SM: one gate per CTA spread over 4 groups + sliced key switch
     int balance_tail = 1;            // K3: the last wave spreads its gates over all SMs (TFHE_B200_BALANCE=0: full CTAs only)
     int ks_tile32 = 1;               // batches that do not fill the SMs with 64-ciphertext tiles take tiles of 32 (TFHE_B200_KS_TILE32=0: off)
@@ -197,8 +198,9 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
                 {
                     constexpr int TMv = NP == 1 ? 0 : 2;
                     const unsigned long long sms = (unsigned long long)ctx->sm_count;
-                    // measured (tools/latency_probe.py): one wave of 148 gates takes 1.95 ms on the latency kernel,
-                    // 592 gates 6.45 ms on the 4-gates-per-CTA kernel, so up to 3 waves the latency kernel also wins
+                    // measured (tools/latency_probe.py, tools/waves_probe.py): one wave of 148 gates takes 1.95 ms on the latency
+                    // kernel, two 3.7-3.9 ms, three 5.6-5.8 ms; K3 with a balanced wave 4.0-4.2 ms at 2 gates per CTA, 4.45-4.61 ms
+                    // at 3 and 5.67 ms at 4 (all with the key switch): ctx->lowlat_waves
                     if constexpr (NP == 2) {
                         // at most one gate per two SMs: a cluster of two CTAs per gate (blind_rotate_cluster.cuh)
                         if (A.count <= (unsigned long long)ctx->max_clusters && ctx->lowlat && ctx->cluster == 2) {   // clock64 phase probe (development)
@@ -232,7 +234,7 @@ int launch_br_np(tfhe_b200_ctx* ctx, const BlindRotateArgs& A, cudaStream_t s) {
                             return 0;
                         }
                     }
-                    if (A.count <= 3 * sms && ctx->lowlat && br_lowlat_smem_bytes<L, NP>(A.n_pad) <= 227 * 1024) {
+                    if (A.count <= (unsigned long long)ctx->lowlat_waves * sms && ctx->lowlat && br_lowlat_smem_bytes<L, NP>(A.n_pad) <= 227 * 1024) {
                         // latency path (blind_rotate_lowlat.cuh): one gate per CTA, one digit polynomial per group
                         auto kern = blind_rotate_lowlat_kernel<L, BGBIT, NP>;
                         const size_t smem = br_lowlat_smem_bytes<L, NP>(A.n_pad);
@@ -497,6 +499,11 @@ int tfhe_b200_create(const tfhe_b200_params* params, int device_id, uint32_t fla
     c->mk_ring = env_int("TFHE_B200_MK_RING", 1);
     c->mk_pw = env_int("TFHE_B200_MK_PW", 1);
     c->lowlat = env_int("TFHE_B200_LOWLAT", 1);
+    // measured (tools/waves_probe.py, profiles/r2/waves_probe_v17.json): with its last wave balanced K3 takes 4.45-4.61 ms for
+    // 297-444 gates (3 per CTA) where three waves of the latency kernel take 5.6-5.8 ms; for 149-296 gates the latency
+    // kernel's two waves (3.7-3.9 ms) still beat K3 with 2 gates per CTA (4.0-4.2 ms) with two pieces, not with one (3.0-3.2 vs 2.6-2.8 ms)
+    // (80-bit set; the 128-bit set keeps three waves: not measured)
+    c->lowlat_waves = std::max(1, env_int("TFHE_B200_LOWLAT_WAVES", P.l == 2 ? (c->NP == 2 ? 2 : 1) : 3));
     c->l2_hint = env_int("TFHE_B200_L2HINT", 0);
     c->l2_persist = env_int("TFHE_B200_L2PERSIST", 0);
     c->cluster = env_int("TFHE_B200_CLUSTER", 1);
