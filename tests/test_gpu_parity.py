@@ -395,3 +395,26 @@ def test_device_resident_batch_is_walked_in_pieces(keys80_small, octx80_small, m
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
     assert np.array_equal(outs[1][0], octx80_small.gate(O.NAND, cts[0], cts[1]))
     assert np.array_equal(outs[1][1][:200], octx80_small.gate(O.MUX, cts[0][:200], cts[1][:200], cts[2][:200]))
+
+
+@pytest.fixture(scope="module")
+def keys128_small():
+    return O.keygen(O.small_params(O.PARAMS_128, 24), 654)
+
+
+@pytest.mark.parametrize("flags", [_cabi.FLAG_SPLIT_FFT, _cabi.FLAG_UNSPLIT_FFT], ids=["split", "unsplit"])
+@pytest.mark.parametrize("count", [3, 74, 75, 149, 444, 445, 601, 700])
+def test_every_batch_size_dispatch_path_equals_oracle_128(keys128_small, flags, count):
+    """The same walk through the dispatch for the 128-bit set (l = 3, Bg = 2^7, api.jl:55-69): cluster kernel with three
+    groups per CTA, latency kernel with six groups (up to 3 gates per SM), the four-gates-per-CTA kernel with its
+    output-stationary step for three digit polynomials per component, balanced last wave, and the key switch over rows padded
+    to the same stride as n = 24 gives.  Every ciphertext against the oracle."""
+    P = keys128_small.params
+    octx = O.Context(keys128_small)
+    ctx = T.Context(n=P.n, l=P.l, bgbit=P.bgbit, t=P.t, basebit=P.basebit, flags=flags)
+    ctx.load_bk(keys128_small.bk); ctx.load_ksk(keys128_small.ksk)
+    bits = np.random.default_rng(count).integers(0, 2, (count, 3)).astype(bool)
+    rng = O.Rng(1000 + count)
+    x, y, z = (O.encrypt(rng, keys128_small, bits[:, i]) for i in range(3))
+    assert np.array_equal(ctx.gate(O.NAND, x, y), octx.gate(O.NAND, x, y))
+    assert np.array_equal(ctx.gate(O.MUX, x, y, z), octx.gate(O.MUX, x, y, z))
