@@ -198,3 +198,17 @@ def test_mk_nand_full_size_ring_kernels_equal_oracle(p, count, nsample, monkeypa
         ok = int(np.sum(O.mk_decrypt(mk, got) == ~(bits[:, 0] & bits[:, 1])))
         print(f"{p} parties: {ok}/{count} gates decrypt to NAND (oracle sample identical)")
         assert ok >= 0.9 * count
+
+
+@pytest.mark.parametrize("mu", [1 << 29, 1 << 30, -(1 << 29), 123456789])
+def test_mk_bootstrap_with_arbitrary_test_vector_value(mu):
+    """mk_bootstrap(bk, ks, mu, x) (mk_internals.jl:512-515) = mk_keyswitch(mk_bootstrap_wo_keyswitch(mu, x)): the seam
+    function takes ANY mu, mk_gate_nand only ever passes 1/8.  tfhe_b200_mk_bootstrap_batch and its two halves against the
+    oracle, 2 parties, short LWE key."""
+    mk = O.mk_keygen(O.small_params(O.MK_PARAMS[2], 6), 2, 61)
+    octx = O.MKContext(mk)
+    ctx = make_mk_ctx(mk)
+    x = O.mk_encrypt(O.Rng(4), mk, [True, False, True])
+    u = ctx.bootstrap_wo_ks(x, mu)
+    assert np.array_equal(u, octx.bootstrap_wo_ks(x, mu))
+    assert np.array_equal(ctx.mk_bootstrap(x, mu), octx.keyswitch(u))

@@ -418,3 +418,15 @@ def test_every_batch_size_dispatch_path_equals_oracle_128(keys128_small, flags, 
     x, y, z = (O.encrypt(rng, keys128_small, bits[:, i]) for i in range(3))
     assert np.array_equal(ctx.gate(O.NAND, x, y), octx.gate(O.NAND, x, y))
     assert np.array_equal(ctx.gate(O.MUX, x, y, z), octx.gate(O.MUX, x, y, z))
+
+
+@pytest.mark.parametrize("mu", [1 << 30, -(1 << 29), 123456789])
+def test_bootstrap_with_arbitrary_test_vector_value(keys80_small, octx80_small, gctx80_small, mu):
+    """bootstrap(bk, ks, mu, x) (bootstrap.jl:92-95) takes ANY mu; the gates only ever pass 1/8.  Both halves and the fused
+    call against the oracle, also on a batch large enough for the four-gates-per-CTA kernel."""
+    rng = O.Rng(77)
+    x = O.encrypt(rng, keys80_small, np.random.default_rng(7).integers(0, 2, 600).astype(bool))
+    u = gctx80_small.bootstrap_wo_ks(x, mu)
+    assert np.array_equal(u, octx80_small.bootstrap_wo_ks(x, mu))
+    assert np.array_equal(gctx80_small.bootstrap(x[:5], mu), octx80_small.bootstrap(x[:5], mu))
+    assert np.array_equal(gctx80_small.bootstrap(x, mu), octx80_small.keyswitch(u))
