@@ -212,3 +212,25 @@ def test_mk_bootstrap_with_arbitrary_test_vector_value(mu):
     u = ctx.bootstrap_wo_ks(x, mu)
     assert np.array_equal(u, octx.bootstrap_wo_ks(x, mu))
     assert np.array_equal(ctx.mk_bootstrap(x, mu), octx.keyswitch(u))
+
+
+def test_multi_device_context_mk_equals_single_device():
+    """tfhe_b200_multi_mk_load_bk / _ksk / _mk_nand_batch / _bootstrap_batch on an MK context: the sharded result (one
+    shard per visible GPU; with one GPU the same threads-and-slices code path) equals the single-device ciphertexts and
+    the oracle's."""
+    mk = O.mk_keygen(O.small_params(O.MK_PARAMS[2], 6), 2, 62)
+    octx = O.MKContext(mk)
+    P = mk.params
+    count = 301
+    bits = np.random.default_rng(62).integers(0, 2, (count, 2)).astype(bool)
+    rng = O.Rng(62)
+    x, y = O.mk_encrypt(rng, mk, bits[:, 0]), O.mk_encrypt(rng, mk, bits[:, 1])
+    want = make_mk_ctx(mk).mk_nand(x, y)
+    assert np.array_equal(want[:16], octx.nand(x[:16], y[:16]))
+    m = _cabi.MultiContext(n=P.n, l=P.l, bgbit=P.bgbit, t=P.t, basebit=P.basebit, parties=2, devices=None)
+    m.load_bk(mk.bk); m.load_ksk(mk.ksk)
+    assert np.array_equal(m.mk_nand(x, y), want)
+    assert np.array_equal(m.mk_nand(x[:1], y[:1]), want[:1])
+    mu = 1 << 30
+    assert np.array_equal(m.bootstrap(x[:9], mu), octx.keyswitch(octx.bootstrap_wo_ks(x[:9], mu)))
+    m.close()

@@ -430,3 +430,15 @@ def test_bootstrap_with_arbitrary_test_vector_value(keys80_small, octx80_small, 
     assert np.array_equal(u, octx80_small.bootstrap_wo_ks(x, mu))
     assert np.array_equal(gctx80_small.bootstrap(x[:5], mu), octx80_small.bootstrap(x[:5], mu))
     assert np.array_equal(gctx80_small.bootstrap(x, mu), octx80_small.keyswitch(u))
+
+
+def test_bad_gate_arguments_are_errors_not_crashes(keys80_small, gctx80_small):
+    """Unknown opcode, a binary gate without its second operand, MUX without its third: TFHE_B200_EINVAL with a message."""
+    n1 = keys80_small.params.n + 1
+    x = np.zeros((2, n1), np.int32)
+    for args in ((99, x, x, None), (O.NAND, x, None, None), (O.MUX, x, x, None), (O.NOT, None, None, None)):
+        with pytest.raises(T.TFHEB200Error) as e:
+            gctx80_small.gate(args[0], args[1], args[2], args[3], count=2)
+        assert e.value.code == _cabi.EINVAL and str(e.value)
+    # the context is still usable afterwards
+    assert gctx80_small.gate(O.NOT, x).shape == (2, n1)
