@@ -234,3 +234,22 @@ def test_multi_device_context_mk_equals_single_device():
     mu = 1 << 30
     assert np.array_equal(m.bootstrap(x[:9], mu), octx.keyswitch(octx.bootstrap_wo_ks(x[:9], mu)))
     m.close()
+
+
+def test_mk_device_pointer_entry_points():
+    """tfhe_b200_mk_nand_batch_dev / tfhe_b200_mk_bootstrap_batch_dev on device-resident ciphertexts and the caller's
+    stream give the ciphertexts of the host-buffer calls."""
+    import torch
+    mk = O.mk_keygen(O.small_params(O.MK_PARAMS[2], 6), 2, 63)
+    ctx = make_mk_ctx(mk)
+    x, y = O.mk_encrypt(O.Rng(5), mk, [True, False, True, True, False]), O.mk_encrypt(O.Rng(6), mk, [True, True, False, False, False])
+    dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    out = torch.empty_like(dx)
+    s = torch.cuda.current_stream().cuda_stream
+    ctx.mk_nand_dev(dx.data_ptr(), dy.data_ptr(), out.data_ptr(), 5, stream=s)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), ctx.mk_nand(x, y))
+    mu = -(1 << 29)
+    ctx.mk_bootstrap_dev(dx.data_ptr(), out.data_ptr(), 5, mu=mu, stream=s)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), ctx.mk_bootstrap(x, mu))

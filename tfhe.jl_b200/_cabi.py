@@ -365,6 +365,9 @@ class Context:
     def mk_nand_dev(self, x_ptr, y_ptr, out_ptr, count, stream=0):
         self._ck(lib().tfhe_b200_mk_nand_batch_dev(self._h, x_ptr, y_ptr, out_ptr, count, stream or None))
 
+    def mk_bootstrap_dev(self, x_ptr, out_ptr, count, mu=1 << 29, stream=0):
+        self._ck(lib().tfhe_b200_mk_bootstrap_batch_dev(self._h, mu, x_ptr, out_ptr, count, stream or None))
+
 
 class MultiContext:
     """One logical evaluation context over several GPUs (tfhe_b200_multi_*): keys replicated at load, every batch cut
