@@ -253,3 +253,27 @@ def test_mk_device_pointer_entry_points():
     ctx.mk_bootstrap_dev(dx.data_ptr(), out.data_ptr(), 5, mu=mu, stream=s)
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy(), ctx.mk_bootstrap(x, mu))
+
+
+def test_mk_device_resident_batch_is_walked_in_pieces(monkeypatch):
+    """tfhe_b200_mk_nand_batch_dev / _mk_bootstrap_batch_dev bound their scratch like the single-key call: with the piece
+    size forced down to one wave of CTAs a ragged 700-gate batch gives the ciphertexts of the one-pass run."""
+    import torch
+    mk = O.mk_keygen(O.small_params(O.MK_PARAMS[2], 3), 2, 64)
+    count = 700
+    bits = np.random.default_rng(64).integers(0, 2, (count, 2)).astype(bool)
+    x, y = O.mk_encrypt(O.Rng(7), mk, bits[:, 0]), O.mk_encrypt(O.Rng(8), mk, bits[:, 1])
+    dx, dy = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    s = torch.cuda.current_stream().cuda_stream
+    res = []
+    for piece in (None, "1"):
+        if piece:
+            monkeypatch.setenv("TFHE_B200_DEV_PIECE", piece)
+        ctx = make_mk_ctx(mk)
+        o1, o2 = torch.empty_like(dx), torch.empty_like(dx)
+        ctx.mk_nand_dev(dx.data_ptr(), dy.data_ptr(), o1.data_ptr(), count, stream=s)
+        ctx.mk_bootstrap_dev(dx.data_ptr(), o2.data_ptr(), count, mu=1 << 30, stream=s)
+        torch.cuda.synchronize()
+        res.append((o1.cpu().numpy(), o2.cpu().numpy()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert np.array_equal(res[1][0][:32], O.MKContext(mk).nand(x[:32], y[:32]))
